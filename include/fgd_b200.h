@@ -1,0 +1,158 @@
+/*
+ * fgd_b200.h -- C ABI of the B200-native batched functional-gradient-descent
+ * (FGD) trajectory optimiser.  libfgd_b200.so exports exactly these symbols.
+ *
+ * The reference (simongroeger/irm_motion_planning) has no FFI; the seam this
+ * library replaces is the jitted operator
+ *     jit_optimize(self, alpha, obstacles, start_config, goal_config) -> alpha
+ *         optimizer_BLS.py:126-213, optimizer_GD.py:68-97 and :172-232
+ * together with the objective it closes over
+ *     Trajectory.compute_trajectory_cost / _g     trajectory.py:271-297
+ *     Trajectory.constraintsFulfilled             trajectory.py:129-137
+ * generalised from ONE trajectory to a batch of B independent trajectories.
+ * Traced inputs of the reference operator (alpha, obstacles, start, goal) are
+ * runtime buffers here; everything the reference closes over (K, dK, J, robot
+ * and hyper-parameters) is fixed at fgd_create() time.
+ *
+ * Conventions
+ *  - plain C types only; all pointers marked d_ are CUDA device pointers owned
+ *    by the caller (PyTorch in the Python host), h_ are host pointers.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *  - every function returns 0 on success, an FgdStatus code otherwise; nothing
+ *    calls exit() (the reference prints "FATAL" and exit(-1), the Python host
+ *    re-creates that behaviour on top of these codes).
+ *  - one host thread per handle; calls on one handle are not re-entrant.
+ *  - all arithmetic is FP32, the reference's precision (JAX default, x64 off).
+ */
+#ifndef FGD_B200_H
+#define FGD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FGD_ABI_VERSION 1
+#define FGD_MAX_T 256            /* time samples / RKHS support points            */
+#define FGD_MAX_OUTER 16         /* length of the gd_lr table                     */
+#define FGD_FSTATE 8             /* floats of resumable state per trajectory      */
+#define FGD_ISTATE 8             /* int32s of resumable state per trajectory      */
+
+typedef enum FgdStatus {
+    FGD_OK = 0,
+    FGD_ERR_INVALID_ARGUMENT = 1,
+    FGD_ERR_UNSUPPORTED_T = 2,        /* T < 2 or T > FGD_MAX_T                    */
+    FGD_ERR_KERNEL_NOT_SYMMETRIC = 3, /* km != km^T or dkm != -dkm^T bit-wise      */
+    FGD_ERR_TOO_MANY_OBSTACLES = 4,   /* count > obstacle_capacity                 */
+    FGD_ERR_CUDA = 5,                 /* see fgd_last_cuda_error()                 */
+    FGD_ERR_NO_DEVICE = 6,
+    FGD_ERR_JOINTS = 7                /* n_joints != 3 (robot.py:31, trajectory.py:42) */
+} FgdStatus;
+
+/* fstate[b][FGD_FSTATE] */
+enum { FGD_F_LAM_SG = 0, FGD_F_LAM_JL = 1, FGD_F_LR = 2, FGD_F_LOSS = 3, FGD_F_TOC = 4, FGD_F_LAST_NEW_LOSS = 5 };
+/* istate[b][FGD_ISTATE] */
+enum { FGD_I_STATUS = 0, FGD_I_OUTER = 1, FGD_I_INNER = 2, FGD_I_INNER_TOTAL = 3, FGD_I_CAND_EVALS = 4,
+       FGD_I_ACCEPTS = 5, FGD_I_FULFILLED = 6, FGD_I_HASH = 7 };
+/* istate[b][FGD_I_STATUS]; a zero-filled state means "fresh, start from lambda_*_constraint" */
+enum { FGD_ST_FRESH = 0, FGD_ST_ACTIVE = 1, FGD_ST_DONE = 2 };
+
+/* Static configuration = everything the reference's optimizer object closes
+ * over (main.py:17-98 flag table). */
+typedef struct FgdConfig {
+    int32_t abi_version;                 /* FGD_ABI_VERSION                                  */
+    int32_t n_timesteps;                 /* --n-timesteps            trajectory.py:34        */
+    int32_t n_joints;                    /* --n-joints, must be 3    robot.py:18             */
+    int32_t obstacle_capacity;           /* max obstacles the device buffer can hold         */
+    int32_t strict_math;                 /* 1: IEEE reciprocal (bit-exact vs oracle), 0: rcp.approx */
+    int32_t max_inner_iteration;         /* optimizer_BLS.py:27                              */
+    int32_t max_outer_iteration;         /* optimizer_BLS.py:28                              */
+    int32_t max_bls_iteration;           /* optimizer_BLS.py:39                              */
+    int32_t constraint_violating_dependant_loss; /* trajectory.py:28                         */
+    int32_t n_gd_lr;                     /* valid entries of gd_lr   optimizer_GD.py:34-38   */
+    float lambda_sg_constraint, lambda_jl_constraint, lambda_constraint_increase;   /* optimizer_BLS.py:32-34 */
+    float lambda_max_cost, lambda_reg;                                              /* optimizer_BLS.py:36-37 */
+    float loop_loss_reduction;                                                      /* optimizer_BLS.py:30    */
+    float eps_position, eps_velocity;                                               /* robot.py:25-26         */
+    float bls_lr_start, bls_alpha, bls_beta_plus, bls_beta_minus;                   /* optimizer_BLS.py:40-43 */
+    float joint_safety_limit;                                                       /* trajectory.py:29       */
+    float max_joint_position, min_joint_position, max_joint_velocity;               /* robot.py:14-16         */
+    float link_length[3];                                                           /* robot.py:19            */
+    float jac[9];                        /* row-major 3x3            trajectory.py:42        */
+    float gd_lr[FGD_MAX_OUTER];          /* --gd-lr                  optimizer_GD.py:38      */
+    const float *h_km;                   /* host, row-major T x T    trajectory.py:40        */
+    const float *h_dkm;                  /* host, row-major T x T    trajectory.py:41        */
+} FgdConfig;
+
+typedef struct FgdHandle FgdHandle;
+
+/* Replaces the optimizer constructors' setup (optimizer_BLS.py:23-48,
+ * optimizer_GD.py:15-45): copies K, dK (re-laid out), J and all scalars to the
+ * current CUDA device.  The caller keeps ownership of the host arrays. */
+int fgd_create(const FgdConfig *cfg, FgdHandle **out);
+int fgd_destroy(FgdHandle *h);
+
+const char *fgd_status_string(int status);
+/* cudaError_t of the last failing CUDA call on this handle (0 if none). */
+int fgd_last_cuda_error(const FgdHandle *h);
+
+/* Replaces passing `self.env.obstacles` as a traced argument
+ * (optimizer_BLS.py:60,79,82,90; environment.py:17-29): uploads `count` (x,y)
+ * pairs into the inactive half of a double-buffered device array with
+ * cudaMemcpyAsync on `stream` and makes it the active set for every launch
+ * enqueued afterwards.  No recompilation, no handle re-creation.
+ * xy_on_device: 0 = host pointer (pinned for true asynchrony), 1 = device. */
+int fgd_set_obstacles_async(FgdHandle *h, const float *xy, int32_t count, int32_t xy_on_device, void *stream);
+int fgd_obstacle_count(const FgdHandle *h);
+
+/* Unit-parity hook = compute_trajectory_cost + compute_trajectory_cost_g +
+ * constraintsFulfilled for B trajectories at given penalty weights
+ * (trajectory.py:271-297,129-137).  Any output pointer may be NULL.
+ *   lambda_max_cost: the reference's static argument (main.py:141-142 calls it
+ *                    with 0 and 1 for the final report); < 0 = the configured value
+ *   d_alpha [B][T][3], d_start/d_goal [B][3]
+ *   d_loss [B], d_toc [B] (obstacle term only), d_grad [B][T][3],
+ *   d_q / d_v [B][T][3] (K alpha J, dK alpha J), d_fulfilled [B] (0/1) */
+int fgd_eval_cost_grad(FgdHandle *h, int32_t B, const float *d_alpha, const float *d_start, const float *d_goal,
+                       float lambda_sg, float lambda_jl, float lambda_max_cost, float *d_loss, float *d_toc,
+                       float *d_grad, float *d_q, float *d_v, int32_t *d_fulfilled, void *stream);
+
+/* Replace BacktrackingLineSearchOptimizer.jit_optimize (optimizer_BLS.py:126-213)
+ * and GradientDescentOptimizer.jit_optimize / jit_dual_optimize
+ * (optimizer_GD.py:68-97 when max_outer_iteration == 1, :172-232 otherwise)
+ * for B trajectories.  d_alpha is updated in place.  d_fstate/d_istate carry the
+ * loop state between calls (zero-fill for a fresh run): each call advances every
+ * unfinished trajectory by at most `max_launch_iters` inner iterations
+ * (< 0: run to completion), re-evaluating the loss at the current obstacle set
+ * first -- the plain loop's "read self.env.obstacles afresh" semantics
+ * (optimizer_BLS.py:79,82,90). */
+int fgd_optimize_bls(FgdHandle *h, int32_t B, float *d_alpha, const float *d_start, const float *d_goal,
+                     float *d_fstate, int32_t *d_istate, int32_t max_launch_iters, void *stream);
+int fgd_optimize_gd(FgdHandle *h, int32_t B, float *d_alpha, const float *d_start, const float *d_goal,
+                    float *d_fstate, int32_t *d_istate, int32_t max_launch_iters, void *stream);
+
+/* Same operators with HOST buffers (what a reference-side binding would call):
+ * H2D of alpha/start/goal, run to completion, D2H of alpha and state, all on
+ * `stream`, synchronised before returning.  use_gd: 0 = BLS, 1 = GD. */
+int fgd_optimize_host(FgdHandle *h, int32_t use_gd, int32_t B, float *h_alpha, const float *h_start,
+                      const float *h_goal, float *h_fstate, int32_t *h_istate, void *stream);
+
+/* Random-restart reduction: trajectories are laid out [n_problems][n_restarts];
+ * for each problem pick the restart with the lowest obstacle cost among the
+ * constraint-fulfilling ones (falls back to lowest cost if none is fulfilled).
+ * d_best_cost [n_problems], d_best_index [n_problems] = index_offset + b. */
+int fgd_argmin_per_problem(FgdHandle *h, int32_t n_problems, int32_t n_restarts, const float *d_fstate,
+                           const int32_t *d_istate, int32_t index_offset, float *d_best_cost,
+                           int32_t *d_best_index, void *stream);
+
+/* Introspection for the harness. */
+int fgd_launch_geometry(const FgdHandle *h, int32_t B, int32_t *grid, int32_t *block, int32_t *smem_bytes,
+                        int32_t *trajectories_per_warp);
+int64_t fgd_kernel_launches(const FgdHandle *h);   /* kernels launched through this handle so far */
+int fgd_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FGD_B200_H */

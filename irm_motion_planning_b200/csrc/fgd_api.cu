@@ -1,0 +1,422 @@
+// fgd_api.cu -- C ABI (include/fgd_b200.h) over the sm_100a kernels.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "fgd_kernels.cuh"
+
+using namespace fgd;
+
+struct FgdHandle {
+    FgdConfig cfg;
+    DevParams base;            // everything except the per-call batch pointers
+    int T, TP, RPL;
+    bool k_in_smem;
+    int device, num_sms, max_smem_optin;
+    float *d_Kt = nullptr, *d_dKt = nullptr;
+    float *d_obs[2] = {nullptr, nullptr};
+    int obs_active = 0, obs_count = 0;
+    unsigned *d_queue = nullptr;
+    cudaEvent_t obs_event = nullptr, launch_event = nullptr;
+    bool obs_event_pending = false, launch_event_pending = false;
+    int last_cuda_error = 0;
+    long long launches = 0;
+    int force_slots = 0;       // FGD_TRAJ_PER_WARP override (tuning)
+    int force_warps = 0;       // FGD_WARPS_PER_CTA override (tuning)
+    // scratch for the host-buffer entry point
+    float *s_alpha = nullptr, *s_start = nullptr, *s_goal = nullptr, *s_fstate = nullptr;
+    int *s_istate = nullptr;
+    int s_cap = 0;
+};
+
+#define CK(call)                                                     \
+    do {                                                             \
+        cudaError_t e_ = (call);                                     \
+        if (e_ != cudaSuccess) { h->last_cuda_error = (int)e_; return FGD_ERR_CUDA; } \
+    } while (0)
+
+namespace {
+
+constexpr int NW = 8;   // warps per CTA
+
+struct Geometry { int S, grid, block, smem; };
+
+template <int RPL, int S, bool STRICT, bool KS>
+cudaError_t launch_opt(const DevParams &p, int grid, size_t smem, cudaStream_t st)
+{
+    auto kern = fgd_optimize_kernel<RPL, S, STRICT, KS, NW>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, NW * 32, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+template <int RPL, int S, bool STRICT, bool KS>
+int occupancy_opt(size_t smem)
+{
+    auto kern = fgd_optimize_kernel<RPL, S, STRICT, KS, NW>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, NW * 32, smem) != cudaSuccess) nb = 1;
+    return nb < 1 ? 1 : nb;
+}
+
+template <int RPL, bool STRICT, bool KS>
+cudaError_t launch_eval(const DevParams &p, const EvalPtrs &e, int grid, size_t smem, cudaStream_t st)
+{
+    auto kern = fgd_eval_kernel<RPL, STRICT, KS, NW>;
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    kern<<<grid, NW * 32, smem, st>>>(p, e);
+    return cudaGetLastError();
+}
+
+// (RPL, S) combinations that are instantiated
+#define FGD_FOR_RPL_S(X) X(1, 1) X(1, 2) X(1, 4) X(2, 1) X(2, 2) X(2, 4) X(4, 1) X(4, 2) X(8, 1)
+
+cudaError_t dispatch_opt(int RPL, int S, bool strict, bool ks, const DevParams &p, int grid, size_t smem, cudaStream_t st)
+{
+#define X(R_, S_)                                                                             \
+    if (RPL == R_ && S == S_) {                                                               \
+        if (ks) return strict ? launch_opt<R_, S_, true, true>(p, grid, smem, st)             \
+                              : launch_opt<R_, S_, false, true>(p, grid, smem, st);           \
+        return strict ? launch_opt<R_, S_, true, false>(p, grid, smem, st)                    \
+                      : launch_opt<R_, S_, false, false>(p, grid, smem, st);                  \
+    }
+    FGD_FOR_RPL_S(X)
+#undef X
+    return cudaErrorInvalidValue;
+}
+
+int dispatch_occ(int RPL, int S, bool strict, bool ks, size_t smem)
+{
+#define X(R_, S_)                                                                             \
+    if (RPL == R_ && S == S_) {                                                               \
+        if (ks) return strict ? occupancy_opt<R_, S_, true, true>(smem) : occupancy_opt<R_, S_, false, true>(smem);   \
+        return strict ? occupancy_opt<R_, S_, true, false>(smem) : occupancy_opt<R_, S_, false, false>(smem);        \
+    }
+    FGD_FOR_RPL_S(X)
+#undef X
+    return 1;
+}
+
+cudaError_t dispatch_eval(int RPL, bool strict, bool ks, const DevParams &p, const EvalPtrs &e, int grid, size_t smem, cudaStream_t st)
+{
+#define X(R_)                                                                                 \
+    if (RPL == R_) {                                                                          \
+        if (ks) return strict ? launch_eval<R_, true, true>(p, e, grid, smem, st) : launch_eval<R_, false, true>(p, e, grid, smem, st);   \
+        return strict ? launch_eval<R_, true, false>(p, e, grid, smem, st) : launch_eval<R_, false, false>(p, e, grid, smem, st);        \
+    }
+    X(1) X(2) X(4) X(8)
+#undef X
+    return cudaErrorInvalidValue;
+}
+
+int max_slots_for(int RPL) { return RPL <= 2 ? 4 : (RPL == 4 ? 2 : 1); }
+
+// Trajectories per warp: the largest S that still leaves >= 16 warps per SM of
+// work (latency hiding first, operand reuse second); overridable for tuning.
+int choose_slots(const FgdHandle *h, int B)
+{
+    const int smax = max_slots_for(h->RPL);
+    if (h->force_slots > 0) {
+        int s = h->force_slots;
+        while (s > smax) s >>= 1;
+        return s < 1 ? 1 : s;
+    }
+    const long long want_warps = (long long)h->num_sms * 16;
+    for (int s = smax; s > 1; s >>= 1)
+        if ((long long)B / s >= want_warps) return s;
+    return 1;
+}
+
+Geometry geometry(const FgdHandle *h, int B, int n_obs)
+{
+    Geometry g;
+    g.S = choose_slots(h, B);
+    g.block = NW * 32;
+    for (;;) {
+        g.smem = (int)make_layout(h->T, h->TP, n_obs, h->k_in_smem, NW * g.S).bytes();
+        if (g.smem <= h->max_smem_optin || g.S == 1) break;
+        g.S >>= 1;
+    }
+    const int occ = dispatch_occ(h->RPL, g.S, h->cfg.strict_math != 0, h->k_in_smem, (size_t)g.smem);
+    const long long need = ((long long)B + (long long)g.S * NW - 1) / ((long long)g.S * NW);
+    const long long cap = (long long)occ * h->num_sms;
+    g.grid = (int)(need < cap ? need : cap);
+    if (g.grid < 1) g.grid = 1;
+    return g;
+}
+
+void fill_params(const FgdHandle *h, DevParams &p, int mode, int B, float *alpha, const float *start, const float *goal,
+                 float *fstate, int *istate, int budget)
+{
+    p = h->base;
+    p.mode = mode; p.B = B; p.budget = budget;
+    p.n_obs = h->obs_count;
+    p.obs = h->d_obs[h->obs_active];
+    p.alpha = alpha; p.start = start; p.goal = goal; p.fstate = fstate; p.istate = istate;
+    p.queue = h->d_queue;
+}
+
+int wait_obstacles(FgdHandle *h, cudaStream_t st)
+{
+    if (h->obs_event_pending) {
+        CK(cudaStreamWaitEvent(st, h->obs_event, 0));
+    }
+    return FGD_OK;
+}
+
+int run_optimize(FgdHandle *h, int mode, int B, float *d_alpha, const float *d_start, const float *d_goal, float *d_fstate,
+                 int *d_istate, int budget, cudaStream_t st)
+{
+    if (!h || B < 0 || (B > 0 && (!d_alpha || !d_start || !d_goal || !d_fstate || !d_istate))) return FGD_ERR_INVALID_ARGUMENT;
+    if (mode == 1 && h->cfg.max_outer_iteration > h->cfg.n_gd_lr) return FGD_ERR_INVALID_ARGUMENT;   // optimizer_GD.py:34-36
+    if (B == 0) return FGD_OK;
+    int rc = wait_obstacles(h, st);
+    if (rc) return rc;
+    DevParams p;
+    fill_params(h, p, mode, B, d_alpha, d_start, d_goal, d_fstate, d_istate, budget);
+    const Geometry g = geometry(h, B, p.n_obs);
+    CK(cudaMemsetAsync(h->d_queue, 0, sizeof(unsigned), st));
+    CK(dispatch_opt(h->RPL, g.S, h->cfg.strict_math != 0, h->k_in_smem, p, g.grid, (size_t)g.smem, st));
+    h->launches += 1;
+    CK(cudaEventRecord(h->launch_event, st));
+    h->launch_event_pending = true;
+    return FGD_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fgd_abi_version(void) { return FGD_ABI_VERSION; }
+
+const char *fgd_status_string(int s)
+{
+    switch (s) {
+        case FGD_OK: return "ok";
+        case FGD_ERR_INVALID_ARGUMENT: return "invalid argument";
+        case FGD_ERR_UNSUPPORTED_T: return "n_timesteps outside [2, 256]";
+        case FGD_ERR_KERNEL_NOT_SYMMETRIC: return "km must be symmetric and dkm antisymmetric (bit-wise)";
+        case FGD_ERR_TOO_MANY_OBSTACLES: return "obstacle count exceeds obstacle_capacity";
+        case FGD_ERR_CUDA: return "CUDA error (see fgd_last_cuda_error)";
+        case FGD_ERR_NO_DEVICE: return "no CUDA device";
+        case FGD_ERR_JOINTS: return "n_joints must be 3";
+        default: return "unknown status";
+    }
+}
+
+int fgd_last_cuda_error(const FgdHandle *h) { return h ? h->last_cuda_error : 0; }
+
+int fgd_create(const FgdConfig *cfg, FgdHandle **out)
+{
+    if (!cfg || !out || cfg->abi_version != FGD_ABI_VERSION || !cfg->h_km || !cfg->h_dkm) return FGD_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    if (cfg->n_joints != 3) return FGD_ERR_JOINTS;
+    const int T = cfg->n_timesteps;
+    if (T < 2 || T > FGD_MAX_T) return FGD_ERR_UNSUPPORTED_T;
+    if (cfg->obstacle_capacity < 1 || cfg->max_outer_iteration < 1 || cfg->max_outer_iteration > FGD_MAX_OUTER ||
+        cfg->n_gd_lr < 0 || cfg->n_gd_lr > FGD_MAX_OUTER || cfg->max_bls_iteration < 1)
+        return FGD_ERR_INVALID_ARGUMENT;
+    // K^T = K and dK^T = -dK bit-wise: lets the backward contraction reuse the staged tiles.
+    for (int i = 0; i < T; ++i)
+        for (int k = 0; k < T; ++k) {
+            const float a = cfg->h_km[i * T + k], b = cfg->h_km[k * T + i];
+            const float c = cfg->h_dkm[i * T + k], d = -cfg->h_dkm[k * T + i];
+            if (!(a == b)) return FGD_ERR_KERNEL_NOT_SYMMETRIC;
+            if (!(c == d)) return FGD_ERR_KERNEL_NOT_SYMMETRIC;
+        }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return FGD_ERR_NO_DEVICE;
+
+    FgdHandle *h = new FgdHandle();
+    h->cfg = *cfg;
+    h->cfg.h_km = nullptr; h->cfg.h_dkm = nullptr;
+    h->T = T;
+    h->RPL = T <= 32 ? 1 : (T <= 64 ? 2 : (T <= 128 ? 4 : 8));
+    h->TP = 32 * h->RPL;
+    auto fail = [&](int code) { fgd_destroy(h); return code; };
+#define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(FGD_ERR_CUDA); } while (0)
+    CKC(cudaGetDevice(&h->device));
+    CKC(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device));
+    CKC(cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+    // K and dK go to shared memory when both fit beside the operand buffers of at least one slot per warp
+    h->k_in_smem = make_layout(T, h->TP, cfg->obstacle_capacity, true, NW).bytes() <= (size_t)h->max_smem_optin && h->RPL <= 4;
+    if (const char *e = std::getenv("FGD_TRAJ_PER_WARP")) h->force_slots = std::atoi(e);
+
+    std::vector<float> kt((size_t)T * h->TP, 0.0f), dkt((size_t)T * h->TP, 0.0f);
+    for (int i = 0; i < T; ++i)
+        for (int k = 0; k < T; ++k) { kt[(size_t)k * h->TP + i] = cfg->h_km[i * T + k]; dkt[(size_t)k * h->TP + i] = cfg->h_dkm[i * T + k]; }
+    CKC(cudaMalloc(&h->d_Kt, kt.size() * 4));
+    CKC(cudaMalloc(&h->d_dKt, dkt.size() * 4));
+    CKC(cudaMemcpy(h->d_Kt, kt.data(), kt.size() * 4, cudaMemcpyHostToDevice));
+    CKC(cudaMemcpy(h->d_dKt, dkt.data(), dkt.size() * 4, cudaMemcpyHostToDevice));
+    for (int i = 0; i < 2; ++i) {
+        CKC(cudaMalloc(&h->d_obs[i], (size_t)cfg->obstacle_capacity * 2 * 4));
+        CKC(cudaMemset(h->d_obs[i], 0, (size_t)cfg->obstacle_capacity * 2 * 4));
+    }
+    CKC(cudaMalloc(&h->d_queue, sizeof(unsigned)));
+    CKC(cudaEventCreateWithFlags(&h->obs_event, cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&h->launch_event, cudaEventDisableTiming));
+#undef CKC
+
+    DevParams &p = h->base;
+    std::memset(&p, 0, sizeof p);
+    p.T = T; p.TP = h->TP;
+    p.max_inner = cfg->max_inner_iteration; p.max_outer = cfg->max_outer_iteration; p.max_bls = cfg->max_bls_iteration;
+    p.cvdl = cfg->constraint_violating_dependant_loss ? 1 : 0;
+    p.lam_sg0 = cfg->lambda_sg_constraint; p.lam_jl0 = cfg->lambda_jl_constraint; p.lam_inc = cfg->lambda_constraint_increase;
+    p.lam_max = cfg->lambda_max_cost; p.lam_reg = cfg->lambda_reg; p.eps_loop = cfg->loop_loss_reduction;
+    p.eps_pos = cfg->eps_position; p.eps_vel = cfg->eps_velocity;
+    p.bls_lr0 = cfg->bls_lr_start; p.bls_alpha = cfg->bls_alpha; p.bls_bp = cfg->bls_beta_plus; p.bls_bm = cfg->bls_beta_minus;
+    p.qmax = cfg->max_joint_position; p.qmin = cfg->min_joint_position; p.vmax = cfg->max_joint_velocity;
+    for (int i = 0; i < 3; ++i) p.link[i] = cfg->link_length[i];
+    for (int i = 0; i < 9; ++i) p.J[i] = cfg->jac[i];
+    for (int i = 0; i < 16; ++i) p.gd_lr[i] = i < cfg->n_gd_lr ? cfg->gd_lr[i] : (cfg->n_gd_lr > 0 ? cfg->gd_lr[cfg->n_gd_lr - 1] : 0.0f);
+    // derived constants: the same FP32 expressions as oracle/fgd_mirror.c derive()
+    p.fT = (float)T;
+    p.oml = 1.0f - p.lam_max;
+    p.inv_T = 1.0f / p.fT;
+    p.w_avg = p.oml * p.inv_T;
+    p.mean_q = 0.5f * (p.qmax + p.qmin);                        // trajectory.py:31
+    const float std_q = 0.5f * (p.qmax - p.mean_q);             // trajectory.py:32
+    p.inv_std = 1.0f / std_q;
+    p.inv_std2 = 1.0f / (std_q * std_q);
+    p.inv_vmax = 1.0f / p.vmax;
+    p.inv_vmax2 = 1.0f / (p.vmax * p.vmax);
+    p.q_hi = cfg->joint_safety_limit * p.qmax;
+    p.q_lo = cfg->joint_safety_limit * p.qmin;
+    p.v_hi = cfg->joint_safety_limit * p.vmax;
+    p.Kt = h->d_Kt; p.dKt = h->d_dKt;
+    *out = h;
+    return FGD_OK;
+}
+
+int fgd_destroy(FgdHandle *h)
+{
+    if (!h) return FGD_OK;
+    cudaFree(h->d_Kt); cudaFree(h->d_dKt); cudaFree(h->d_obs[0]); cudaFree(h->d_obs[1]); cudaFree(h->d_queue);
+    cudaFree(h->s_alpha); cudaFree(h->s_start); cudaFree(h->s_goal); cudaFree(h->s_fstate); cudaFree(h->s_istate);
+    if (h->obs_event) cudaEventDestroy(h->obs_event);
+    if (h->launch_event) cudaEventDestroy(h->launch_event);
+    delete h;
+    return FGD_OK;
+}
+
+int fgd_set_obstacles_async(FgdHandle *h, const float *xy, int32_t count, int32_t on_device, void *stream)
+{
+    if (!h || count < 0 || (count > 0 && !xy)) return FGD_ERR_INVALID_ARGUMENT;
+    if (count > h->cfg.obstacle_capacity) return FGD_ERR_TOO_MANY_OBSTACLES;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int next = h->obs_active ^ 1;
+    // the half being overwritten may still be read by the launch before the previous swap
+    if (h->launch_event_pending) CK(cudaStreamWaitEvent(st, h->launch_event, 0));
+    if (count > 0)
+        CK(cudaMemcpyAsync(h->d_obs[next], xy, (size_t)count * 2 * 4, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(h->obs_event, st));
+    h->obs_event_pending = true;
+    h->obs_active = next;
+    h->obs_count = count;
+    return FGD_OK;
+}
+
+int fgd_obstacle_count(const FgdHandle *h) { return h ? h->obs_count : -1; }
+
+int fgd_eval_cost_grad(FgdHandle *h, int32_t B, const float *d_alpha, const float *d_start, const float *d_goal,
+                       float lambda_sg, float lambda_jl, float lambda_max_cost, float *d_loss, float *d_toc, float *d_grad,
+                       float *d_q, float *d_v, int32_t *d_fulfilled, void *stream)
+{
+    if (!h || B < 0 || (B > 0 && (!d_alpha || !d_start || !d_goal))) return FGD_ERR_INVALID_ARGUMENT;
+    if (B == 0) return FGD_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = wait_obstacles(h, st);
+    if (rc) return rc;
+    DevParams p;
+    fill_params(h, p, 0, B, const_cast<float *>(d_alpha), d_start, d_goal, nullptr, nullptr, -1);
+    if (lambda_max_cost >= 0.0f) {      // static argument of compute_trajectory_cost (trajectory.py:271)
+        p.lam_max = lambda_max_cost; p.oml = 1.0f - p.lam_max; p.w_avg = p.oml * p.inv_T;
+    }
+    EvalPtrs e{lambda_sg, lambda_jl, d_loss, d_toc, d_grad, d_q, d_v, d_fulfilled};
+    const size_t smem = make_layout(h->T, h->TP, p.n_obs, h->k_in_smem, NW).bytes();
+    long long need = ((long long)B + NW - 1) / NW, cap = (long long)h->num_sms * 4;
+    const int grid = (int)(need < cap ? need : cap);
+    CK(dispatch_eval(h->RPL, h->cfg.strict_math != 0, h->k_in_smem, p, e, grid, smem, st));
+    h->launches += 1;
+    return FGD_OK;
+}
+
+int fgd_optimize_bls(FgdHandle *h, int32_t B, float *d_alpha, const float *d_start, const float *d_goal, float *d_fstate,
+                     int32_t *d_istate, int32_t max_launch_iters, void *stream)
+{
+    return run_optimize(h, 0, B, d_alpha, d_start, d_goal, d_fstate, d_istate, max_launch_iters, (cudaStream_t)stream);
+}
+
+int fgd_optimize_gd(FgdHandle *h, int32_t B, float *d_alpha, const float *d_start, const float *d_goal, float *d_fstate,
+                    int32_t *d_istate, int32_t max_launch_iters, void *stream)
+{
+    return run_optimize(h, 1, B, d_alpha, d_start, d_goal, d_fstate, d_istate, max_launch_iters, (cudaStream_t)stream);
+}
+
+int fgd_optimize_host(FgdHandle *h, int32_t use_gd, int32_t B, float *h_alpha, const float *h_start, const float *h_goal,
+                      float *h_fstate, int32_t *h_istate, void *stream)
+{
+    if (!h || B < 0 || (B > 0 && (!h_alpha || !h_start || !h_goal || !h_fstate || !h_istate))) return FGD_ERR_INVALID_ARGUMENT;
+    if (B == 0) return FGD_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (B > h->s_cap) {
+        cudaFree(h->s_alpha); cudaFree(h->s_start); cudaFree(h->s_goal); cudaFree(h->s_fstate); cudaFree(h->s_istate);
+        h->s_alpha = h->s_start = h->s_goal = h->s_fstate = nullptr; h->s_istate = nullptr; h->s_cap = 0;
+        CK(cudaMalloc(&h->s_alpha, (size_t)B * h->T * 3 * 4));
+        CK(cudaMalloc(&h->s_start, (size_t)B * 3 * 4));
+        CK(cudaMalloc(&h->s_goal, (size_t)B * 3 * 4));
+        CK(cudaMalloc(&h->s_fstate, (size_t)B * FGD_FSTATE * 4));
+        CK(cudaMalloc(&h->s_istate, (size_t)B * FGD_ISTATE * 4));
+        h->s_cap = B;
+    }
+    CK(cudaMemcpyAsync(h->s_alpha, h_alpha, (size_t)B * h->T * 3 * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->s_start, h_start, (size_t)B * 3 * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->s_goal, h_goal, (size_t)B * 3 * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->s_fstate, h_fstate, (size_t)B * FGD_FSTATE * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->s_istate, h_istate, (size_t)B * FGD_ISTATE * 4, cudaMemcpyHostToDevice, st));
+    int rc = run_optimize(h, use_gd ? 1 : 0, B, h->s_alpha, h->s_start, h->s_goal, h->s_fstate, h->s_istate, -1, st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h_alpha, h->s_alpha, (size_t)B * h->T * 3 * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_fstate, h->s_fstate, (size_t)B * FGD_FSTATE * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_istate, h->s_istate, (size_t)B * FGD_ISTATE * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return FGD_OK;
+}
+
+int fgd_argmin_per_problem(FgdHandle *h, int32_t n_problems, int32_t n_restarts, const float *d_fstate, const int32_t *d_istate,
+                           int32_t index_offset, float *d_best_cost, int32_t *d_best_index, void *stream)
+{
+    if (!h || n_problems < 0 || n_restarts < 1 || (n_problems > 0 && (!d_fstate || !d_istate || !d_best_cost || !d_best_index)))
+        return FGD_ERR_INVALID_ARGUMENT;
+    if (n_problems == 0) return FGD_OK;
+    const int block = 256, per = block / 32;
+    const int grid = (n_problems + per - 1) / per;
+    fgd_argmin_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(n_problems, n_restarts, d_fstate, d_istate, index_offset, d_best_cost, d_best_index);
+    CK(cudaGetLastError());
+    h->launches += 1;
+    return FGD_OK;
+}
+
+int fgd_launch_geometry(const FgdHandle *h, int32_t B, int32_t *grid, int32_t *block, int32_t *smem_bytes, int32_t *traj_per_warp)
+{
+    if (!h || B < 1) return FGD_ERR_INVALID_ARGUMENT;
+    const Geometry g = geometry(h, B, h->obs_count);
+    if (grid) *grid = g.grid;
+    if (block) *block = g.block;
+    if (smem_bytes) *smem_bytes = g.smem;
+    if (traj_per_warp) *traj_per_warp = g.S;
+    return FGD_OK;
+}
+
+int64_t fgd_kernel_launches(const FgdHandle *h) { return h ? h->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,177 @@
+"""The C mirror oracle (fixed summation order, what the CUDA kernels are compared with
+bit-exactly) against the line-by-line NumPy oracle and its committed vectors.  CPU only."""
+import numpy as np
+import pytest
+
+from oracle import fgd_numpy as O
+from oracle import mirror as M
+
+OBS, START, GOAL = O.DEFAULT_OBSTACLES, O.DEFAULT_START, O.DEFAULT_GOAL
+
+
+@pytest.fixture(scope="module")
+def tm():
+    return O.TrajectoryModel(O.Hyper())
+
+
+def _mirror(tm, mode="bls", hp=None, obs=OBS):
+    return M.Mirror(hp or tm.hp, tm.km, tm.dkm, tm.jac, obs, mode)
+
+
+def _rel(x, y):
+    return float(np.linalg.norm(np.asarray(x, np.float64) - y) / np.linalg.norm(y))
+
+
+@pytest.mark.parametrize("li", [0, 1])
+def test_per_evaluation_parity_well_conditioned(tm, oracle_vectors, li):
+    """Tolerance: loss rel <= 1e-4 (measured ~1e-7), gradient rel <= 1e-4
+    (measured ~3e-7), q/v within 1e-5 abs of the FP64 oracle."""
+    v = oracle_vectors
+    lam = v["lam"][li]
+    e = _mirror(tm).eval(v["alpha_smooth"], v["start"], v["goal"], float(lam[0]), float(lam[1]))
+    k = f"smooth_l{li}_f64"
+    np.testing.assert_allclose(e["loss"], v[k + "_loss"], rtol=2e-6)
+    for b in range(len(e["loss"])):
+        assert _rel(e["grad"][b], v[k + "_grad"][b]) < 5e-6
+    assert np.abs(e["q"] - v[k + "_q"]).max() < 1e-5 and np.abs(e["v"] - v[k + "_v"]).max() < 1e-4
+    assert np.array_equal(e["fulfilled"].astype(bool), v[k + "_ful"])
+
+
+@pytest.mark.parametrize("li", [0, 1])
+def test_per_evaluation_parity_ill_conditioned(tm, oracle_vectors, li):
+    """On the reference's own LU-fitted alpha0 (|alpha| ~ 2e3, cond(K) ~ 1e9 in FP32) any FP32
+    evaluation is ~1e-3 away from FP64; the mirror must be no further than 4x the NumPy FP32 oracle's gap."""
+    v = oracle_vectors
+    lam = v["lam"][li]
+    e = _mirror(tm).eval(v["alpha_fitted"], v["start"], v["goal"], float(lam[0]), float(lam[1]))
+    k32, k64 = f"fitted_l{li}_f32", f"fitted_l{li}_f64"
+    gap_q = np.abs(v[k32 + "_q"] - v[k64 + "_q"]).max()
+    gap_v = np.abs(v[k32 + "_v"] - v[k64 + "_v"]).max()
+    assert np.abs(e["q"] - v[k64 + "_q"]).max() <= 4 * max(gap_q, 1e-5)
+    assert np.abs(e["v"] - v[k64 + "_v"]).max() <= 4 * max(gap_v, 1e-5)
+    gaps = [_rel(v[k32 + "_grad"][b], v[k64 + "_grad"][b]) for b in range(len(e["loss"]))]
+    for b in range(len(e["loss"])):
+        assert _rel(e["grad"][b], v[k64 + "_grad"][b]) <= max(1e-4, 4 * max(gaps))
+        assert abs(e["loss"][b] - v[k64 + "_loss"][b]) <= 4 * max(abs(v[k32 + "_loss"] - v[k64 + "_loss"]).max(), 1e-4 * abs(v[k64 + "_loss"][b]))
+
+
+def test_sincos_accuracy():
+    """The oracle's explicit sin/cos (shared algorithm with the kernels) is within 2 ulp over the
+    angle range a 3-joint arm with limits [-1,2] can reach, and sane far outside it."""
+    import ctypes as C
+    lib = M.lib()
+    tmod = O.TrajectoryModel(O.Hyper())
+    # exercise through fk: a single-sample check via eval's q is indirect, so test the identity directly
+    x = np.linspace(-12, 12, 20001).astype(np.float32)
+    hp = O.Hyper()
+    # evaluate via a tiny trajectory whose q rows are (x, 0, 0): use J = I, K = I
+    T = 50
+    eye = np.eye(T, dtype=np.float32)
+    hp1 = O.Hyper(link_length=[1.0, 0.0, 0.0])
+    m = M.Mirror(hp1, eye, np.zeros((T, T), np.float32), np.eye(3, dtype=np.float32), np.zeros((1, 2), np.float32))
+    worst = 0.0
+    for i in range(0, len(x) - T, T):
+        a = np.zeros((1, T, 3), np.float32); a[0, :, 0] = x[i:i + T]
+        # one obstacle at the origin: cost = 0.8/(0.5+0.5*(cos^2+sin^2)) = 0.8 exactly iff sin^2+cos^2 == 1
+        e = m.eval(a, np.zeros(3, np.float32), np.zeros(3, np.float32), 0.0, 0.0)
+        worst = max(worst, abs(float(e["toc"][0]) - 0.8))
+    assert worst < 5e-7
+
+
+def test_default_problem_end_to_end(tm, reference_results):
+    """Same verdict / costs / joint angles as the reference's shipped result:
+    fulfilled, avg & max cost within 1e-2 relative, joint angles within 5e-2 rad."""
+    m = _mirror(tm)
+    a0 = tm.init_trajectory(START, GOAL)
+    a, fs, is_ = m.optimize(a0[None], START, GOAL)
+    assert is_[0, M.I_STATUS] == M.ST_DONE and is_[0, M.I_FULFILLED] == 1
+    avg, mx, ok = O.final_report(tm, a[0], OBS, START, GOAL)
+    assert ok and abs(avg - 1.685) / 1.685 < 1e-2 and abs(mx - 2.196) / 2.196 < 1e-2
+    assert np.abs(tm.evaluate(a[0], tm.km) - reference_results["trajectory_result"]).max() < 5e-2
+    # obstacle term reported by the mirror = the NumPy oracle's at the same alpha
+    toc = tm.obstacle_cost(tm.evaluate(a[0], tm.km), OBS, 0.5)
+    assert abs(fs[0, M.F_TOC] - toc) < 1e-4
+
+
+def test_first_steps_identical_to_numpy_oracle(tm):
+    """Up to the chaotic divergence the two restatements take the same decisions: the
+    first accepted step sizes of the default run coincide."""
+    a0 = tm.init_trajectory(START, GOAL)
+    _, log = O.bls_optimize(tm, a0, OBS, START, GOAL)
+    m = _mirror(tm)
+    fs, is_ = m.new_state(1)
+    a = a0[None].copy()
+    lrs = []
+    for _ in range(10):
+        a, fs, is_ = m.optimize(a, START, GOAL, fs, is_, budget=1)
+        lrs.append(float(fs[0, M.F_LR]) / 1.2)
+    np.testing.assert_allclose(lrs, log.lrs[:10], rtol=1e-6)
+
+
+def test_budgeted_launches_equal_one_launch(tm):
+    """Splitting a run into launches of k inner iterations is bit-identical to a single launch
+    (state round-trips through fstate/istate) -- the property the dynamic-environment mode relies on."""
+    rng = np.random.default_rng(3)
+    start = rng.uniform(-0.9, 1.9, (8, 3)).astype(np.float32)
+    goal = rng.uniform(-0.9, 1.9, (8, 3)).astype(np.float32)
+    a0 = np.stack([tm.init_trajectory(s, g) for s, g in zip(start, goal)])
+    for mode in ("bls", "gd"):
+        m = _mirror(tm, mode)
+        a_ref, fs_ref, is_ref = m.optimize(a0, start, goal)
+        a, fs, is_ = a0.copy(), *m.new_state(8)
+        for _ in range(10000):
+            a, fs, is_ = m.optimize(a, start, goal, fs, is_, budget=7)
+            if (is_[:, M.I_STATUS] == M.ST_DONE).all():
+                break
+        assert np.array_equal(a, a_ref) and np.array_equal(is_, is_ref)
+        assert np.array_equal(fs[:, :5], fs_ref[:, :5])
+
+
+def test_batch_statistics_match_numpy_oracle(tm):
+    """End-to-end on 32 random problems: fulfilment rate, final obstacle cost and iteration
+    counts of the mirror agree in distribution with the NumPy oracle run in FP32 and in FP64.
+    Individual runs diverge chaotically, and the fulfilment RATE itself depends
+    on the evaluation noise of the executor (measured on 48 problems: NumPy/BLAS FP32 0.73,
+    NumPy FP64 0.83, mirror 0.83), so the mirror must fall inside the band the two span."""
+    rng = np.random.default_rng(7)
+    n = 32
+    start = rng.uniform(-0.9, 1.9, (n, 3)).astype(np.float32)
+    goal = rng.uniform(-0.9, 1.9, (n, 3)).astype(np.float32)
+    a0 = np.stack([tm.init_trajectory(s, g) for s, g in zip(start, goal)])
+    a, fs, is_ = _mirror(tm).optimize(a0, start, goal)
+    tm64 = O.TrajectoryModel(O.Hyper(), dtype=np.float64)
+    stats = {}
+    for name, model in (("f32", tm), ("f64", tm64)):
+        ful, toc, it = [], [], []
+        for b in range(n):
+            an, log = O.bls_optimize(model, a0[b].astype(model.dt), OBS, start[b], goal[b])
+            ful.append(log.fulfilled); it.append(log.inner_iters)
+            toc.append(float(model.obstacle_cost(model.evaluate(an, model.km), OBS, 0.5)))
+        stats[name] = (np.array(ful), np.array(toc), np.array(it))
+    rate = is_[:, M.I_FULFILLED].mean()
+    rates = [stats[k][0].mean() for k in stats]
+    assert min(rates) - 0.15 <= rate <= max(rates) + 0.15, (rate, rates)
+    ful64, toc64, it64 = stats["f64"]
+    both = ful64 & (is_[:, M.I_FULFILLED] == 1)
+    assert both.sum() >= n // 2
+    assert np.median(np.abs(fs[both, M.F_TOC] - toc64[both]) / toc64[both]) < 2e-2
+    its = [stats[k][2].mean() for k in stats]
+    assert 0.7 * min(its) < is_[:, M.I_INNER_TOTAL].mean() < 1.4 * max(its)
+
+
+def test_dynamic_obstacles_schedule(tm):
+    """Obstacle swaps at inner-iteration boundaries (plain-loop semantics, optimizer_BLS.py:79,82,90):
+    mirror with budgeted launches == NumPy oracle with the same schedule, for the first swaps."""
+    rng = np.random.default_rng(11)
+    sets = [OBS.astype(np.float32), (OBS + rng.uniform(-0.3, 0.3, OBS.shape)).astype(np.float32)]
+    a0 = tm.init_trajectory(START, GOAL)
+    _, log = O.bls_optimize(tm, a0, sets[0], START, GOAL, obstacle_schedule=lambda k: sets[(k // 4) % 2])
+    m = _mirror(tm)
+    a, fs, is_ = a0[None].copy(), *m.new_state(1)
+    lrs = []
+    for k in range(3):
+        m.set_obstacles(sets[k % 2])
+        for _ in range(4):
+            a, fs, is_ = m.optimize(a, START, GOAL, fs, is_, budget=1)
+            lrs.append(float(fs[0, M.F_LR]) / 1.2)
+    np.testing.assert_allclose(lrs[:8], log.lrs[:8], rtol=1e-6)

@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the batched FGD hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W [--workload c2|c1|c3|c4|c5] [--impl reference]
+
+A "step" is one pass of the hot path over one batch of synthetic input: every
+trajectory of the batch is optimised to completion (all outer / inner / line
+search iterations) by the persistent sm_100a kernel.  Default workload = config 2
+of BASELINE.json (fixed-step GD, default scene, 4096 random-init trajectories per
+GPU).  Prints ONE JSON line (rank 0).  See DESIGN.md section 6 for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "optimized trajectories/sec"
+UNIT = "trajectories/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override (0 = the configuration's size)")
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--cpu-seconds", type=float, default=10.0, help="budget of the bounded CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--strict-math", action="store_true")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------
+# helpers
+# --------------------------------------------------------------------------
+
+def hp_view(args_ns, T):
+    hp = type("HP", (), dict(vars(args_ns)))()
+    hp.n_timesteps = T
+    return hp
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the GPU is under load (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ts, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7 or not (t0 <= ts <= t1 + 0.06):
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(wl, traj, alpha0, start, goal, seconds, threads=0):
+    """The C mirror oracle (a port of the reference algorithm) on the host cores, on a bounded
+    sample of the same workload."""
+    from oracle import mirror as M
+    m = M.Mirror(hp_view(wl.args, traj.N_timesteps), traj.km, traj.dkm, traj.jac, wl.obstacles, wl.mode)
+    cores = M.max_threads() if threads <= 0 else threads
+    n0 = min(len(alpha0), max(cores * 2, 16))
+    t = time.perf_counter()
+    m.optimize(alpha0[:n0], start[:n0], goal[:n0], nthreads=threads)
+    rate = n0 / max(time.perf_counter() - t, 1e-6)
+    n = int(min(len(alpha0), max(n0, rate * seconds)))
+    t = time.perf_counter()
+    _, fs, is_ = m.optimize(alpha0[:n], start[:n], goal[:n], nthreads=threads)
+    dt = time.perf_counter() - t
+    return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"first {n} trajectories of the {wl.name} batch, C mirror oracle (oracle/fgd_mirror.c), OpenMP over trajectories, {dt:.1f} s",
+            "fgd_iters_per_s": float(is_[:, M.I_INNER_TOTAL].sum() / dt)}, n, dt
+
+
+# --------------------------------------------------------------------------
+# reference arm: the reference algorithm on the host cores
+# --------------------------------------------------------------------------
+
+def run_reference(a, rank, world):
+    if rank != 0:
+        return
+    from irm_motion_planning_b200.trajectory import Trajectory
+    from irm_motion_planning_b200.workloads import initial_alpha, make_workload
+    wl = make_workload(a.workload, B=a.batch or None, seed=a.seed)
+    traj = Trajectory(wl.args, create_handle=False)
+    alpha0, start, goal = initial_alpha(wl, traj, a.seed)
+    # each step: a bounded sample, sized so the whole run stays within a few minutes
+    per_step = max(2.0, min(a.cpu_seconds, 120.0 / max(1, a.steps + a.warmup)))
+    times, n_used, info = [], 0, None
+    for i in range(a.warmup + a.steps):
+        info, n, dt = cpu_baseline(wl, traj, alpha0, start, goal, per_step)
+        if i >= a.warmup:
+            times.append(dt); n_used = n
+    value = n_used * len(times) / sum(times)
+    info["value"] = value
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(wl, traj, len(alpha0), note=f"each step = {n_used} trajectories on {info['cores']} host threads"),
+            "cpu_baseline": info,
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def config_dict(wl, traj, B, **extra):
+    d = {"workload": f"{wl.name}: {wl.description}", "optimizer": wl.mode, "trajectories_per_gpu": int(B),
+         "n_timesteps": traj.N_timesteps, "n_obstacles": int(len(wl.obstacles)), "l2_flush_between_steps": True}
+    d.update(extra)
+    return d
+
+
+# --------------------------------------------------------------------------
+# B200 arm
+# --------------------------------------------------------------------------
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.impl == "reference":
+        run_reference(a, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from irm_motion_planning_b200 import backend
+    from irm_motion_planning_b200.batch import BatchedFGD, gather_best, shard_range
+    from irm_motion_planning_b200.trajectory import Trajectory
+    from irm_motion_planning_b200.workloads import flops_total, initial_alpha, make_workload, obstacle_swap
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the FGD hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    strong = a.workload == "c5"
+    wl = make_workload(a.workload, B=a.batch or None, seed=a.seed + (0 if strong else rank))
+    traj = Trajectory(wl.args, strict_math=a.strict_math)
+    traj.set_obstacles(wl.obstacles)
+    alpha0, start, goal = initial_alpha(wl, traj, a.seed + (0 if strong else rank))
+    prob_lo = 0
+    if strong and world > 1:                       # shard whole problems (all restarts of a problem on one rank)
+        prob_lo, prob_hi = shard_range(wl.n_problems, rank, world)
+        sl = slice(prob_lo * wl.n_restarts, prob_hi * wl.n_restarts)
+        alpha0, start, goal = alpha0[sl], start[sl], goal[sl]
+    n_prob_local = (len(alpha0) // wl.n_restarts) if wl.n_problems else 0
+    B, T = len(alpha0), traj.N_timesteps
+    eng = BatchedFGD(traj, wl.mode)
+    h = traj.handle
+
+    n_total = a.warmup + a.steps
+    a0_dev = torch.as_tensor(alpha0, device=dev)
+    s_dev = torch.as_tensor(start, device=dev).contiguous()
+    g_dev = torch.as_tensor(goal, device=dev).contiguous()
+    # inputs of every step are resident in HBM before the timed region (one alpha buffer per step,
+    # recycled for very large batches)
+    n_buf = n_total if B * T * 12 * n_total < 8e9 else 2
+    bufs = [a0_dev.clone() for _ in range(n_buf)]
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
+    swaps = [torch.as_tensor(wl.obstacles).pin_memory()] + [torch.as_tensor(obstacle_swap(k, a.seed)).pin_memory() for k in range(1, 64)] \
+        if a.workload == "c4" else None
+
+    def one_step(buf):
+        """Launch the hot path for one batch; returns (fstate, istate)."""
+        fs, is_ = eng.new_state(B)
+        if a.workload == "c4":
+            for k in range(10000):
+                h.set_obstacles(swaps[k % len(swaps)])
+                eng.optimize_device(buf, s_dev, g_dev, fs, is_, max_launch_iters=8)
+                if bool((is_[:, backend.I_STATUS] == backend.ST_DONE).all()):
+                    break
+        else:
+            eng.optimize_device(buf, s_dev, g_dev, fs, is_)
+        if wl.n_problems:
+            cost, idx = eng.best_per_problem(type("R", (), {"fstate": fs, "istate": is_})(), n_prob_local, wl.n_restarts,
+                                             index_offset=prob_lo * wl.n_restarts)
+            gather_best(cost, idx)                 # the single NCCL collective of the sweep
+        return fs, is_
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    for i in range(a.warmup):
+        if n_buf < n_total:
+            bufs[i % n_buf].copy_(a0_dev)
+        one_step(bufs[i % n_buf])
+        flush.zero_()
+    barrier()
+    launches0 = h.kernel_launches()
+    t_load0 = time.perf_counter()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    last = None
+    wall0 = time.perf_counter()
+    for i in range(a.steps):
+        buf = bufs[(a.warmup + i) % n_buf]
+        if n_buf < n_total:
+            buf.copy_(a0_dev)
+        flush.zero_()                               # evict the previous step's lines from L2 (outside the event pair)
+        ev[i][0].record()
+        last = one_step(buf)
+        ev[i][1].record()
+    barrier()
+    wall1 = time.perf_counter()
+    launches = h.kernel_launches() - launches0
+    step_ms = [s.elapsed_time(e) for s, e in ev]
+    total_s = sum(step_ms) * 1e-3
+    t_max = torch.tensor([total_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
+    total_s = float(t_max.item())
+
+    fs, is_ = last[0].cpu().numpy(), last[1].cpu().numpy()
+    inner, cand = is_[:, backend.I_INNER_TOTAL], is_[:, backend.I_CAND_EVALS]
+    outer = np.maximum(1, is_[:, backend.I_OUTER] + is_[:, backend.I_FULFILLED])
+    assert (is_[:, backend.I_STATUS] == backend.ST_DONE).all(), "a timed step left unfinished trajectories"
+    O_eff = len(wl.obstacles)
+    flops_step = flops_total(wl.mode, T, O_eff, inner, cand, outer)
+    counts = torch.tensor([float(B), float(inner.sum()), flops_step], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+    n_traj_all, n_iter_all, flops_all = [float(x) for x in counts.tolist()]
+    value = n_traj_all * a.steps / total_s
+
+    # soak: the same step repeated (untimed) so nvidia-smi sees the clocks this kernel runs at
+    t_soak = time.perf_counter()
+    while time.perf_counter() - t_soak < 1.0:
+        one_step(bufs[0])
+        torch.cuda.synchronize()
+    t_load1 = time.perf_counter()
+    clocks = sampler.stop(t_load0, t_load1) if rank == 0 else None
+
+    # end to end through the host-buffer C-ABI call (pinned host memory, H2D + D2H inside the timing)
+    e2e = None
+    if not a.no_e2e and a.workload != "c4":
+        pin = lambda x: torch.as_tensor(x).pin_memory()
+        a_pin, s_pin, g_pin = pin(alpha0), pin(start), pin(goal)
+        out_a = torch.empty_like(a_pin).pin_memory()
+        out_f = torch.empty(B, backend.FSTATE, dtype=torch.float32).pin_memory()
+        out_i = torch.empty(B, backend.ISTATE, dtype=torch.int32).pin_memory()
+        for _ in range(max(1, min(a.warmup, 2))):
+            eng.optimize_pinned(a_pin, s_pin, g_pin, out_a, out_f, out_i)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            eng.optimize_pinned(a_pin, s_pin, g_pin, out_a, out_f, out_i)
+        barrier()
+        e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+        h2d = B * T * 12 + 2 * B * 12 + B * (backend.FSTATE + backend.ISTATE) * 4
+        d2h = B * T * 12 + B * (backend.FSTATE + backend.ISTATE) * 4
+        e2e = {"value": n_traj_all * a.steps / float(e2e_s.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "api": "fgd_optimize_host via BatchedFGD.optimize_pinned"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak = h.measure_fp32_peak()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    kern_s = total_s / a.steps
+    achieved = flops_all / max(world, 1) / kern_s * 1e-12      # per GPU
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(a.workload)
+    except Exception:
+        pass
+    hbm_bytes = B * (2 * T * 12 + 2 * 12 + 2 * (backend.FSTATE + backend.ISTATE) * 4)
+    roofline = {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+                "traffic": traffic,
+                "peak_source": "FFMA probe kernel measured in this run (fgd_measure_fp32_peak); MEASURED_PEAKS.json has no FP32 CUDA-core figure; "
+                               "nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4",
+                "flops": "algorithmic FLOPs of the reference algorithm per launch (SURVEY 8d: F_grad, F_cost per consumed evaluation) / CUDA-event time",
+                "hbm": {"algorithmic_bytes_per_launch": int(hbm_bytes), "achieved_gbs": hbm_bytes / kern_s * 1e-9,
+                        "peak_gbs": peaks.get("hbm_gbs"), "note": "HBM is not the bound: ~25 B per trajectory-iteration"}}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": 1e3 * total_s / a.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(wl, traj, B, trajectories_per_warp=h.launch_geometry(B)["trajectories_per_warp"],
+                                  math="strict" if a.strict_math else "fast (rcp.approx)"),
+            "fgd_iters_per_s": n_iter_all * a.steps / total_s,
+            "mean_inner_iters": float(inner.mean()), "fulfilled_frac": float(is_[:, backend.I_FULFILLED].mean()),
+            "wall_ms_per_step": 1e3 * (wall1 - wall0) / a.steps,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline}
+
+    if world == 1 and not a.no_cpu_baseline:
+        line["cpu_baseline"], _, _ = cpu_baseline(wl, traj, alpha0, start, goal, a.cpu_seconds)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

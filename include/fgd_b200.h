@@ -150,6 +150,9 @@ int fgd_argmin_per_problem(FgdHandle *h, int32_t n_problems, int32_t n_restarts,
 int fgd_launch_geometry(const FgdHandle *h, int32_t B, int32_t *grid, int32_t *block, int32_t *smem_bytes,
                         int32_t *trajectories_per_warp);
 int64_t fgd_kernel_launches(const FgdHandle *h);   /* kernels launched through this handle so far */
+/* FP32 FFMA throughput of the current device (TFLOP/s, best of 5 launches of a
+ * pure-FFMA kernel): the measured denominator of the harness's roofline.frac. */
+int fgd_measure_fp32_peak(FgdHandle *h, double *tflops_out, void *stream);
 int fgd_abi_version(void);
 
 #ifdef __cplusplus

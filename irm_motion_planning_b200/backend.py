@@ -49,6 +49,7 @@ EXPORTED_SYMBOLS = (
     "fgd_create", "fgd_destroy", "fgd_status_string", "fgd_last_cuda_error", "fgd_set_obstacles_async",
     "fgd_obstacle_count", "fgd_eval_cost_grad", "fgd_optimize_bls", "fgd_optimize_gd", "fgd_optimize_host",
     "fgd_argmin_per_problem", "fgd_launch_geometry", "fgd_kernel_launches", "fgd_abi_version",
+    "fgd_measure_fp32_peak",
 )
 
 _lib = None
@@ -82,6 +83,7 @@ def load_library(path: Optional[str] = None):
     lib.fgd_launch_geometry.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     lib.fgd_kernel_launches.argtypes = [vp]
     lib.fgd_kernel_launches.restype = C.c_int64
+    lib.fgd_measure_fp32_peak.argtypes = [vp, C.POINTER(C.c_double), vp]
     if lib.fgd_abi_version() != FGD_ABI_VERSION:
         raise RuntimeError("libfgd_b200.so ABI version mismatch; rebuild")
     if path is None:
@@ -231,6 +233,11 @@ class Handle:
         self._check(self._lib.fgd_launch_geometry(self._h, B, C.byref(g), C.byref(b), C.byref(s), C.byref(t)),
                     "fgd_launch_geometry")
         return dict(grid=g.value, block=b.value, smem_bytes=s.value, trajectories_per_warp=t.value)
+
+    def measure_fp32_peak(self) -> float:
+        out = C.c_double()
+        self._check(self._lib.fgd_measure_fp32_peak(self._h, C.byref(out), self._stream()), "fgd_measure_fp32_peak")
+        return float(out.value)
 
     def kernel_launches(self) -> int:
         return int(self._lib.fgd_kernel_launches(self._h))

@@ -419,4 +419,31 @@ int fgd_launch_geometry(const FgdHandle *h, int32_t B, int32_t *grid, int32_t *b
 
 int64_t fgd_kernel_launches(const FgdHandle *h) { return h ? h->launches : 0; }
 
+int fgd_measure_fp32_peak(FgdHandle *h, double *tflops_out, void *stream)
+{
+    if (!h || !tflops_out) return FGD_ERR_INVALID_ARGUMENT;
+    cudaStream_t st = (cudaStream_t)stream;
+    float *sink = nullptr;
+    CK(cudaMalloc(&sink, 4));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    const int grid = h->num_sms * 8, iters = 4096;
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {          // first rep warms up, best of the rest
+        CK(cudaEventRecord(e0, st));
+        fgd_ffma_peak_kernel<<<grid, 256, 0, st>>>(iters, 1.0f + rep, sink);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(e1, st));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = (double)grid * 256 * (double)iters * 16 * 8 * 2;
+        if (rep > 0 && ms > 0.f) { const double t = flops / (ms * 1e-3) * 1e-12; if (t > best) best = t; }
+        h->launches += 1;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
+    *tflops_out = best;
+    return FGD_OK;
+}
+
 }  // extern "C"

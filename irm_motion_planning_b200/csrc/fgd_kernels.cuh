@@ -440,4 +440,25 @@ __global__ void fgd_argmin_kernel(int n_problems, int n_restarts, const float *_
     }
 }
 
+// ---------------------------------------------------------------------------
+// FP32 roofline probe: 8 independent FFMA chains per thread, nothing else.
+// MEASURED_PEAKS.json has no FP32 CUDA-core figure, so the harness measures the
+// denominator of roofline.frac on the same GPU, in the same run.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fgd_ffma_peak_kernel(int iters, float seed, float *sink)
+{
+    float a0 = seed + threadIdx.x, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+    const float m = 0.999f, c = 1e-3f;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
+            a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
+        }
+    }
+    const float r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (r == 123456.789f) sink[0] = r;
+}
+
 }  // namespace fgd

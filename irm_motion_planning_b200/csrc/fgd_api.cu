@@ -14,7 +14,7 @@ using namespace fgd;
 struct FgdHandle {
     FgdConfig cfg;
     DevParams base;            // everything except the per-call batch pointers
-    int T, TP, RPL;
+    int T, TP, LPT, R;
     bool k_in_smem;
     int device, num_sms, max_smem_optin;
     float *d_Kt = nullptr, *d_dKt = nullptr;
@@ -25,8 +25,6 @@ struct FgdHandle {
     bool obs_event_pending = false, launch_event_pending = false;
     int last_cuda_error = 0;
     long long launches = 0;
-    int force_slots = 0;       // FGD_TRAJ_PER_WARP override (tuning)
-    int force_warps = 0;       // FGD_WARPS_PER_CTA override (tuning)
     // scratch for the host-buffer entry point
     float *s_alpha = nullptr, *s_start = nullptr, *s_goal = nullptr, *s_fstate = nullptr;
     int *s_istate = nullptr;
@@ -41,111 +39,95 @@ struct FgdHandle {
 
 namespace {
 
-constexpr int NW = 8;   // warps per CTA
+struct Geometry { int gpw, grid, block, smem; };
 
-struct Geometry { int S, grid, block, smem; };
+// lane mapping by trajectory length: LPT lanes per trajectory, R adjacent rows per lane (TP = LPT*R >= T)
+struct Mapping { int LPT, R; };
+inline Mapping mapping_for(int T) { return T <= 32 ? Mapping{8, 4} : (T <= 64 ? Mapping{16, 4} : (T <= 128 ? Mapping{32, 4} : Mapping{32, 8})); }
 
-template <int RPL, int S, bool STRICT, bool KS>
+// (LPT, R, KS, NW, MINB): the instantiated kernels.  NW warps per CTA, MINB = min CTAs per SM (register cap).
+#define FGD_FOR_CONFIGS(X) X(8, 4, true, 4, 4) X(16, 4, true, 4, 4) X(32, 4, true, 4, 4) X(32, 8, false, 4, 2)
+
+template <int LPT, int R, bool STRICT, bool KS, int NW, int MINB>
 cudaError_t launch_opt(const DevParams &p, int grid, size_t smem, cudaStream_t st)
 {
-    auto kern = fgd_optimize_kernel<RPL, S, STRICT, KS, NW>;
+    auto kern = fgd_optimize_kernel<LPT, R, STRICT, KS, NW, MINB>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, NW * 32, smem, st>>>(p);
     return cudaGetLastError();
 }
 
-template <int RPL, int S, bool STRICT, bool KS>
+template <int LPT, int R, bool STRICT, bool KS, int NW, int MINB>
 int occupancy_opt(size_t smem)
 {
-    auto kern = fgd_optimize_kernel<RPL, S, STRICT, KS, NW>;
+    auto kern = fgd_optimize_kernel<LPT, R, STRICT, KS, NW, MINB>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int nb = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, NW * 32, smem) != cudaSuccess) nb = 1;
     return nb < 1 ? 1 : nb;
 }
 
-template <int RPL, bool STRICT, bool KS>
+template <int LPT, int R, bool STRICT, bool KS, int NW>
 cudaError_t launch_eval(const DevParams &p, const EvalPtrs &e, int grid, size_t smem, cudaStream_t st)
 {
-    auto kern = fgd_eval_kernel<RPL, STRICT, KS, NW>;
+    auto kern = fgd_eval_kernel<LPT, R, STRICT, KS, NW>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     kern<<<grid, NW * 32, smem, st>>>(p, e);
     return cudaGetLastError();
 }
 
-// (RPL, S) combinations that are instantiated
-#define FGD_FOR_RPL_S(X) X(1, 1) X(1, 2) X(1, 4) X(2, 1) X(2, 2) X(2, 4) X(4, 1) X(4, 2) X(8, 1)
-
-cudaError_t dispatch_opt(int RPL, int S, bool strict, bool ks, const DevParams &p, int grid, size_t smem, cudaStream_t st)
+int warps_per_cta(int LPT, int R)
 {
-#define X(R_, S_)                                                                             \
-    if (RPL == R_ && S == S_) {                                                               \
-        if (ks) return strict ? launch_opt<R_, S_, true, true>(p, grid, smem, st)             \
-                              : launch_opt<R_, S_, false, true>(p, grid, smem, st);           \
-        return strict ? launch_opt<R_, S_, true, false>(p, grid, smem, st)                    \
-                      : launch_opt<R_, S_, false, false>(p, grid, smem, st);                  \
-    }
-    FGD_FOR_RPL_S(X)
+#define X(L_, R_, KS_, NW_, MB_) if (LPT == L_ && R == R_) return NW_;
+    FGD_FOR_CONFIGS(X)
+#undef X
+    return 4;
+}
+
+cudaError_t dispatch_opt(int LPT, int R, bool strict, const DevParams &p, int grid, size_t smem, cudaStream_t st)
+{
+#define X(L_, R_, KS_, NW_, MB_)                                                             \
+    if (LPT == L_ && R == R_)                                                                 \
+        return strict ? launch_opt<L_, R_, true, KS_, NW_, MB_>(p, grid, smem, st)            \
+                      : launch_opt<L_, R_, false, KS_, NW_, MB_>(p, grid, smem, st);
+    FGD_FOR_CONFIGS(X)
 #undef X
     return cudaErrorInvalidValue;
 }
 
-int dispatch_occ(int RPL, int S, bool strict, bool ks, size_t smem)
+int dispatch_occ(int LPT, int R, bool strict, size_t smem)
 {
-#define X(R_, S_)                                                                             \
-    if (RPL == R_ && S == S_) {                                                               \
-        if (ks) return strict ? occupancy_opt<R_, S_, true, true>(smem) : occupancy_opt<R_, S_, false, true>(smem);   \
-        return strict ? occupancy_opt<R_, S_, true, false>(smem) : occupancy_opt<R_, S_, false, false>(smem);        \
-    }
-    FGD_FOR_RPL_S(X)
+#define X(L_, R_, KS_, NW_, MB_)                                                             \
+    if (LPT == L_ && R == R_)                                                                 \
+        return strict ? occupancy_opt<L_, R_, true, KS_, NW_, MB_>(smem) : occupancy_opt<L_, R_, false, KS_, NW_, MB_>(smem);
+    FGD_FOR_CONFIGS(X)
 #undef X
     return 1;
 }
 
-cudaError_t dispatch_eval(int RPL, bool strict, bool ks, const DevParams &p, const EvalPtrs &e, int grid, size_t smem, cudaStream_t st)
+cudaError_t dispatch_eval(int LPT, int R, bool strict, const DevParams &p, const EvalPtrs &e, int grid, size_t smem, cudaStream_t st)
 {
-#define X(R_)                                                                                 \
-    if (RPL == R_) {                                                                          \
-        if (ks) return strict ? launch_eval<R_, true, true>(p, e, grid, smem, st) : launch_eval<R_, false, true>(p, e, grid, smem, st);   \
-        return strict ? launch_eval<R_, true, false>(p, e, grid, smem, st) : launch_eval<R_, false, false>(p, e, grid, smem, st);        \
-    }
-    X(1) X(2) X(4) X(8)
+#define X(L_, R_, KS_, NW_, MB_)                                                             \
+    if (LPT == L_ && R == R_)                                                                 \
+        return strict ? launch_eval<L_, R_, true, KS_, NW_>(p, e, grid, smem, st)             \
+                      : launch_eval<L_, R_, false, KS_, NW_>(p, e, grid, smem, st);
+    FGD_FOR_CONFIGS(X)
 #undef X
     return cudaErrorInvalidValue;
-}
-
-int max_slots_for(int RPL) { return RPL <= 2 ? 4 : (RPL == 4 ? 2 : 1); }
-
-// Trajectories per warp: the largest S that still leaves >= 16 warps per SM of
-// work (latency hiding first, operand reuse second); overridable for tuning.
-int choose_slots(const FgdHandle *h, int B)
-{
-    const int smax = max_slots_for(h->RPL);
-    if (h->force_slots > 0) {
-        int s = h->force_slots;
-        while (s > smax) s >>= 1;
-        return s < 1 ? 1 : s;
-    }
-    const long long want_warps = (long long)h->num_sms * 16;
-    for (int s = smax; s > 1; s >>= 1)
-        if ((long long)B / s >= want_warps) return s;
-    return 1;
 }
 
 Geometry geometry(const FgdHandle *h, int B, int n_obs)
 {
     Geometry g;
-    g.S = choose_slots(h, B);
-    g.block = NW * 32;
-    for (;;) {
-        g.smem = (int)make_layout(h->T, h->TP, n_obs, h->k_in_smem, NW * g.S).bytes();
-        if (g.smem <= h->max_smem_optin || g.S == 1) break;
-        g.S >>= 1;
-    }
-    const int occ = dispatch_occ(h->RPL, g.S, h->cfg.strict_math != 0, h->k_in_smem, (size_t)g.smem);
-    const long long need = ((long long)B + (long long)g.S * NW - 1) / ((long long)g.S * NW);
+    const int nw = warps_per_cta(h->LPT, h->R);
+    g.gpw = 32 / h->LPT;
+    g.block = nw * 32;
+    g.smem = (int)make_layout(h->T, h->TP, n_obs, h->k_in_smem, nw * g.gpw).bytes();
+    const int occ = dispatch_occ(h->LPT, h->R, h->cfg.strict_math != 0, (size_t)g.smem);
+    const long long per_cta = (long long)nw * g.gpw;
+    const long long need = ((long long)B + per_cta - 1) / per_cta;
     const long long cap = (long long)occ * h->num_sms;
     g.grid = (int)(need < cap ? need : cap);
     if (g.grid < 1) g.grid = 1;
@@ -183,7 +165,7 @@ int run_optimize(FgdHandle *h, int mode, int B, float *d_alpha, const float *d_s
     fill_params(h, p, mode, B, d_alpha, d_start, d_goal, d_fstate, d_istate, budget);
     const Geometry g = geometry(h, B, p.n_obs);
     CK(cudaMemsetAsync(h->d_queue, 0, sizeof(unsigned), st));
-    CK(dispatch_opt(h->RPL, g.S, h->cfg.strict_math != 0, h->k_in_smem, p, g.grid, (size_t)g.smem, st));
+    CK(dispatch_opt(h->LPT, h->R, h->cfg.strict_math != 0, p, g.grid, (size_t)g.smem, st));
     h->launches += 1;
     CK(cudaEventRecord(h->launch_event, st));
     h->launch_event_pending = true;
@@ -238,16 +220,15 @@ int fgd_create(const FgdConfig *cfg, FgdHandle **out)
     h->cfg = *cfg;
     h->cfg.h_km = nullptr; h->cfg.h_dkm = nullptr;
     h->T = T;
-    h->RPL = T <= 32 ? 1 : (T <= 64 ? 2 : (T <= 128 ? 4 : 8));
-    h->TP = 32 * h->RPL;
+    { const Mapping m = mapping_for(T); h->LPT = m.LPT; h->R = m.R; }
+    h->TP = h->LPT * h->R;
     auto fail = [&](int code) { fgd_destroy(h); return code; };
 #define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(FGD_ERR_CUDA); } while (0)
     CKC(cudaGetDevice(&h->device));
     CKC(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device));
     CKC(cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
     // K and dK go to shared memory when both fit beside the operand buffers of at least one slot per warp
-    h->k_in_smem = make_layout(T, h->TP, cfg->obstacle_capacity, true, NW).bytes() <= (size_t)h->max_smem_optin && h->RPL <= 4;
-    if (const char *e = std::getenv("FGD_TRAJ_PER_WARP")) h->force_slots = std::atoi(e);
+    h->k_in_smem = h->R <= 4;     // T <= 128: 2*T*TP*4 B <= 128 KB; T = 256 streams K rows from L2
 
     std::vector<float> kt((size_t)T * h->TP, 0.0f), dkt((size_t)T * h->TP, 0.0f);
     for (int i = 0; i < T; ++i)
@@ -342,10 +323,11 @@ int fgd_eval_cost_grad(FgdHandle *h, int32_t B, const float *d_alpha, const floa
         p.lam_max = lambda_max_cost; p.oml = 1.0f - p.lam_max; p.w_avg = p.oml * p.inv_T;
     }
     EvalPtrs e{lambda_sg, lambda_jl, d_loss, d_toc, d_grad, d_q, d_v, d_fulfilled};
-    const size_t smem = make_layout(h->T, h->TP, p.n_obs, h->k_in_smem, NW).bytes();
-    long long need = ((long long)B + NW - 1) / NW, cap = (long long)h->num_sms * 4;
+    const int nw = warps_per_cta(h->LPT, h->R), per_cta = nw * (32 / h->LPT);
+    const size_t smem = make_layout(h->T, h->TP, p.n_obs, h->k_in_smem, per_cta).bytes();
+    long long need = ((long long)B + per_cta - 1) / per_cta, cap = (long long)h->num_sms * 4;
     const int grid = (int)(need < cap ? need : cap);
-    CK(dispatch_eval(h->RPL, h->cfg.strict_math != 0, h->k_in_smem, p, e, grid, smem, st));
+    CK(dispatch_eval(h->LPT, h->R, h->cfg.strict_math != 0, p, e, grid, smem, st));
     h->launches += 1;
     return FGD_OK;
 }
@@ -413,7 +395,7 @@ int fgd_launch_geometry(const FgdHandle *h, int32_t B, int32_t *grid, int32_t *b
     if (grid) *grid = g.grid;
     if (block) *block = g.block;
     if (smem_bytes) *smem_bytes = g.smem;
-    if (traj_per_warp) *traj_per_warp = g.S;
+    if (traj_per_warp) *traj_per_warp = g.gpw;
     return FGD_OK;
 }
 

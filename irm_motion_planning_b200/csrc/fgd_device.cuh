@@ -1,14 +1,17 @@
 // fgd_device.cuh -- device-side building blocks of the batched FGD iteration (sm_100a).
 //
-// Mapping: one warp runs S independent trajectories as
-// autonomous state machines.  Lane L owns time samples t = L + 32 r (r < RPL):
-// the RKHS contraction produces row t of q = K alpha J and v = dK alpha J in the
-// lane that then does forward kinematics, the obstacle potential and the penalty
-// terms for that sample -- no shared-memory round trip between the two.  K and dK
-// are staged once per CTA in shared memory (transposed, so a warp reads 32
-// consecutive floats), the operand rows (alpha' or the q/v-gradients) sit in
-// per-warp shared buffers and are broadcast.  Reductions over t are lane-serial
-// followed by a 5-level xor butterfly, the order the mirror oracle reproduces.
+// Mapping.  A trajectory is owned by a GROUP of LPT lanes
+// (LPT = 8, 16 or 32; a warp carries 32/LPT independent trajectories side by
+// side).  Lane l of the group owns the R adjacent time samples t = R*l .. R*l+R-1
+// (R = 4 or 8).  The RKHS contraction produces rows t of q = K alpha J and
+// v = dK alpha J in the lane that then does forward kinematics, the obstacle
+// potential and the penalty terms for those samples -- no shared-memory round
+// trip between the two.  K and dK are staged once per CTA in shared memory,
+// transposed, so a lane fetches its R row entries of column k with one or two
+// LDS.128 and the groups of a warp share the load by broadcast; the operand rows
+// (alpha' or the q/v-gradients) sit in per-group shared buffers and are broadcast
+// inside the group.  Reductions over t: lane-serial over the R rows, then an
+// xor butterfly over the LPT lanes -- the order the mirror oracle reproduces.
 //
 // Compiled with -fmad=false: every fused multiply-add is an explicit fmaf(), so
 // the operation sequence is the documented one (bit-exact against the oracle in
@@ -48,7 +51,7 @@ struct EvalPtrs {
     int *fulfilled;
 };
 
-// warp-uniform per-trajectory scalars (shared memory, one per slot)
+// group-uniform per-trajectory scalars (shared memory, one per group)
 struct Slot {
     int traj, status, outer, inner, inner_total, cand_evals, accepts, ful, j, done_iters;
     unsigned hash;
@@ -56,11 +59,49 @@ struct Slot {
     float start[3], goal[3];
 };
 
-__device__ __forceinline__ float wsum(float v)
+// lane geometry of one trajectory group
+template <int LPT>
+struct Group {
+    int lane, gl, base;
+    unsigned mask;
+    __device__ __forceinline__ Group()
+    {
+        lane = threadIdx.x & 31;
+        gl = lane & (LPT - 1);
+        base = lane & ~(LPT - 1);
+        mask = (LPT == 32) ? FULL : (((1u << LPT) - 1u) << base);
+    }
+};
+
+template <int LPT>
+__device__ __forceinline__ float gsum(float v, unsigned mask)
 {
 #pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) v = v + __shfl_xor_sync(FULL, v, o);
+    for (int o = LPT / 2; o >= 1; o >>= 1) v = v + __shfl_xor_sync(mask, v, o);
     return v;
+}
+
+template <int LPT>
+__device__ __forceinline__ float gmax(float v, unsigned mask)
+{
+#pragma unroll
+    for (int o = LPT / 2; o >= 1; o >>= 1) v = fmaxf(v, __shfl_xor_sync(mask, v, o));
+    return v;
+}
+
+template <int LPT>
+__device__ __forceinline__ int gmin_int(int v, unsigned mask)
+{
+#pragma unroll
+    for (int o = LPT / 2; o >= 1; o >>= 1) v = min(v, __shfl_xor_sync(mask, v, o));
+    return v;
+}
+
+template <int LPT>
+__device__ __forceinline__ bool gall(bool pred, unsigned mask)
+{
+    if constexpr (LPT == 32) return __all_sync(FULL, pred);
+    return (__ballot_sync(mask, pred) & mask) == mask;
 }
 
 __device__ __forceinline__ float ss3(float a, float b, float c) { return fmaf(c, c, fmaf(b, b, a * a)); }
@@ -101,54 +142,57 @@ __device__ __forceinline__ void sincos_cw(float x, float &S, float &C)
 }
 
 // ---------------------------------------------------------------------------
-// RKHS contraction for S trajectories of one warp:
-//   y1[s][r][a] = sum_k K [t_r][k] * x1[s][k][a]      (trajectory.py:65 / :295)
-//   y2[s][r][a] = sum_k dK[t_r][k] * x2[s][k][a]
+// RKHS contraction for the trajectory of this lane's group:
+//   y1[r][a] = sum_k K [t_r][k] * x1[k][a]      (trajectory.py:65 / :295)
+//   y2[r][a] = sum_k dK[t_r][k] * x2[k][a]
 // k ascending, one fmaf per term.  K rows come from shared memory (KS) or L2.
+// kp / dp point at this lane's first row entry of column 0.
 // ---------------------------------------------------------------------------
-template <int RPL, int S, bool KS>
-__device__ __forceinline__ void contract(const float *__restrict__ Kt, const float *__restrict__ dKt, int T, int TP, int lane,
-                                         const float4 *const (&x1)[S], const float4 *const (&x2)[S],
-                                         float (&y1)[S][RPL][3], float (&y2)[S][RPL][3])
+template <int R, bool KS>
+__device__ __forceinline__ void contract(const float *__restrict__ kp, const float *__restrict__ dp, int T, int TP,
+                                         const float4 *__restrict__ x1, const float4 *__restrict__ x2,
+                                         float (&y1)[R][3], float (&y2)[R][3])
 {
 #pragma unroll
-    for (int s = 0; s < S; ++s)
+    for (int r = 0; r < R; ++r)
 #pragma unroll
-        for (int r = 0; r < RPL; ++r)
-#pragma unroll
-            for (int a = 0; a < 3; ++a) { y1[s][r][a] = 0.0f; y2[s][r][a] = 0.0f; }
+        for (int a = 0; a < 3; ++a) { y1[r][a] = 0.0f; y2[r][a] = 0.0f; }
 
-    const float *kp = Kt + lane, *dp = dKt + lane;
-#pragma unroll 2
+#pragma unroll 5
     for (int k = 0; k < T; ++k) {
-        float kv[RPL], dv[RPL];
+        float kv[R], dv[R];
 #pragma unroll
-        for (int r = 0; r < RPL; ++r) {
-            if constexpr (KS) { kv[r] = kp[32 * r]; dv[r] = dp[32 * r]; }
-            else { kv[r] = __ldg(kp + 32 * r); dv[r] = __ldg(dp + 32 * r); }
+        for (int r4 = 0; r4 < R; r4 += 4) {
+            float4 a, b;
+            if constexpr (KS) {
+                a = *reinterpret_cast<const float4 *>(kp + r4);
+                b = *reinterpret_cast<const float4 *>(dp + r4);
+            } else {
+                a = __ldg(reinterpret_cast<const float4 *>(kp + r4));
+                b = __ldg(reinterpret_cast<const float4 *>(dp + r4));
+            }
+            kv[r4] = a.x; kv[r4 + 1] = a.y; kv[r4 + 2] = a.z; kv[r4 + 3] = a.w;
+            dv[r4] = b.x; dv[r4 + 1] = b.y; dv[r4 + 2] = b.z; dv[r4 + 3] = b.w;
         }
         kp += TP; dp += TP;
+        const float4 xa = x1[k];
+        const float4 xb = x2[k];
 #pragma unroll
-        for (int s = 0; s < S; ++s) {
-            const float4 xa = x1[s][k];
-            const float4 xb = x2[s][k];
-#pragma unroll
-            for (int r = 0; r < RPL; ++r) {
-                y1[s][r][0] = fmaf(kv[r], xa.x, y1[s][r][0]);
-                y1[s][r][1] = fmaf(kv[r], xa.y, y1[s][r][1]);
-                y1[s][r][2] = fmaf(kv[r], xa.z, y1[s][r][2]);
-                y2[s][r][0] = fmaf(dv[r], xb.x, y2[s][r][0]);
-                y2[s][r][1] = fmaf(dv[r], xb.y, y2[s][r][1]);
-                y2[s][r][2] = fmaf(dv[r], xb.z, y2[s][r][2]);
-            }
+        for (int r = 0; r < R; ++r) {
+            y1[r][0] = fmaf(kv[r], xa.x, y1[r][0]);
+            y1[r][1] = fmaf(kv[r], xa.y, y1[r][1]);
+            y1[r][2] = fmaf(kv[r], xa.z, y1[r][2]);
+            y2[r][0] = fmaf(dv[r], xb.x, y2[r][0]);
+            y2[r][1] = fmaf(dv[r], xb.y, y2[r][1]);
+            y2[r][2] = fmaf(dv[r], xb.z, y2[r][2]);
         }
     }
 }
 
 // Per-lane rows kept between the cost phase and the gradient phase.
-template <int RPL>
+template <int R>
 struct Rows {
-    float q[RPL][3], v[RPL][3], sn[RPL][3], cs[RPL][3], gx[RPL], gy[RPL];
+    float q[R][3], v[R][3], sn[R][3], cs[R][3], gx[R], gy[R];
     float d0[3], dT[3];   // q[0]-start, q[T-1]-goal (meaningful in the owning lanes)
     int amax;
 };
@@ -159,53 +203,62 @@ struct Rows {
 //   trajectory.py:271-281 (total), :81-88 (max/mean), :183-255 (penalties),
 //   :129-137 + robot.py:90-113 (constraint predicates), robot.py:29-36 (fk),
 //   environment.py:32-58 (obstacle potential and its (x,y)-gradient).
+// The obstacle loop accumulates sum 1/den and sum d/den^2; the constant factors
+// 0.8 and -0.8 of environment.py:43,57 are applied once per sample.
 // ---------------------------------------------------------------------------
-template <int RPL, bool STRICT>
-__device__ __forceinline__ void cost_phase(const DevParams &p, const float2 *__restrict__ sObs, int lane,
-                                           const float (&yq)[RPL][3], const float (&yv)[RPL][3],
+template <int LPT, int R, bool STRICT>
+__device__ __forceinline__ void cost_phase(const DevParams &p, const float2 *__restrict__ sObs, const Group<LPT> &G,
+                                           const float (&yq)[R][3], const float (&yv)[R][3],
                                            const float *start, const float *goal, float lam_sg, float lam_jl,
-                                           Rows<RPL> &R, float &loss, float &toc, int &ful)
+                                           Rows<R> &Rw, float &loss, float &toc, int &ful)
 {
     const int T = p.T;
-    float cost[RPL];
-    float part_c = 0.0f, part_p = 0.0f, part_v = 0.0f;
-    unsigned maxbits = 0u;
+    const int t0 = G.gl * R;
+    float cost[R];
+    float part_c = 0.0f, part_p = 0.0f, part_v = 0.0f, lmax = 0.0f;
     bool lim_ok = true;
+    float x[R], y[R], sr[R], sx[R], sy[R];
 #pragma unroll
-    for (int r = 0; r < RPL; ++r) {
-        const int t = lane + 32 * r;
-        const bool valid = t < T;
+    for (int r = 0; r < R; ++r) {
 #pragma unroll
         for (int b = 0; b < 3; ++b) {   // (M @ alpha) @ J
-            R.q[r][b] = fmaf(yq[r][2], p.J[6 + b], fmaf(yq[r][1], p.J[3 + b], yq[r][0] * p.J[b]));
-            R.v[r][b] = fmaf(yv[r][2], p.J[6 + b], fmaf(yv[r][1], p.J[3 + b], yv[r][0] * p.J[b]));
+            Rw.q[r][b] = fmaf(yq[r][2], p.J[6 + b], fmaf(yq[r][1], p.J[3 + b], yq[r][0] * p.J[b]));
+            Rw.v[r][b] = fmaf(yv[r][2], p.J[6 + b], fmaf(yv[r][1], p.J[3 + b], yv[r][0] * p.J[b]));
         }
-        const float c1 = R.q[r][0], c2 = c1 + R.q[r][1], c3 = c2 + R.q[r][2];
-        sincos_cw(c1, R.sn[r][0], R.cs[r][0]);
-        sincos_cw(c2, R.sn[r][1], R.cs[r][1]);
-        sincos_cw(c3, R.sn[r][2], R.cs[r][2]);
-        const float x = fmaf(p.link[2], R.cs[r][2], fmaf(p.link[1], R.cs[r][1], p.link[0] * R.cs[r][0]));
-        const float y = fmaf(p.link[2], R.sn[r][2], fmaf(p.link[1], R.sn[r][1], p.link[0] * R.sn[r][0]));
-        float c = 0.0f, ax = 0.0f, ay = 0.0f;
-        const int n_obs = p.n_obs;
-#pragma unroll 4
-        for (int o = 0; o < n_obs; ++o) {
-            const float2 ob = sObs[o];
-            const float dx = x - ob.x, dy = y - ob.y;
+        const float c1 = Rw.q[r][0], c2 = c1 + Rw.q[r][1], c3 = c2 + Rw.q[r][2];
+        sincos_cw(c1, Rw.sn[r][0], Rw.cs[r][0]);
+        sincos_cw(c2, Rw.sn[r][1], Rw.cs[r][1]);
+        sincos_cw(c3, Rw.sn[r][2], Rw.cs[r][2]);
+        x[r] = fmaf(p.link[2], Rw.cs[r][2], fmaf(p.link[1], Rw.cs[r][1], p.link[0] * Rw.cs[r][0]));
+        y[r] = fmaf(p.link[2], Rw.sn[r][2], fmaf(p.link[1], Rw.sn[r][1], p.link[0] * Rw.sn[r][0]));
+        sr[r] = 0.0f; sx[r] = 0.0f; sy[r] = 0.0f;
+    }
+    // obstacle potential: all R samples of this lane against every obstacle
+    const int n_obs = p.n_obs;
+#pragma unroll 2
+    for (int o = 0; o < n_obs; ++o) {
+        const float2 ob = sObs[o];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const float dx = x[r] - ob.x, dy = y[r] - ob.y;
             const float n = fmaf(dy, dy, dx * dx);
             const float den = fmaf(0.5f, n, 0.5f);
             const float rr = rcp<STRICT>(den);
-            const float cc = 0.8f * rr;
-            c = c + cc;
-            const float w = -(cc * rr);
-            ax = fmaf(w, dx, ax);
-            ay = fmaf(w, dy, ay);
+            sr[r] = sr[r] + rr;
+            const float r2 = rr * rr;
+            sx[r] = fmaf(r2, dx, sx[r]);
+            sy[r] = fmaf(r2, dy, sy[r]);
         }
-        cost[r] = c; R.gx[r] = ax; R.gy[r] = ay;
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const bool valid = (t0 + r) < T;
+        const float c = 0.8f * sr[r];
+        cost[r] = c; Rw.gx[r] = -0.8f * sx[r]; Rw.gy[r] = -0.8f * sy[r];
         float e3[3], f3[3];
 #pragma unroll
         for (int b = 0; b < 3; ++b) {
-            const float qb = R.q[r][b], vb = R.v[r][b];
+            const float qb = Rw.q[r][b], vb = Rw.v[r][b];
             const float u = (qb - p.mean_q) * p.inv_std;
             const bool m = p.cvdl ? (qb > p.q_hi || qb < p.q_lo) : true;
             e3[b] = m ? 0.5f * (u * u) : 0.0f;
@@ -218,42 +271,40 @@ __device__ __forceinline__ void cost_phase(const DevParams &p, const float2 *__r
             part_c = part_c + c;
             part_p = part_p + ((e3[0] + e3[1]) + e3[2]);
             part_v = part_v + ((f3[0] + f3[1]) + f3[2]);
-            maxbits = max(maxbits, __float_as_uint(c));   // c >= 0: uint order == float order
+            lmax = fmaxf(lmax, c);          // c >= 0
         }
     }
     // max / first argmax / mean over t
-    const float maxc = __uint_as_float(__reduce_max_sync(FULL, maxbits));
+    const float maxc = gmax<LPT>(lmax, G.mask);
     int cand = 0x7fffffff;
 #pragma unroll
-    for (int r = RPL - 1; r >= 0; --r) {
-        const int t = lane + 32 * r;
-        if (t < T && cost[r] == maxc) cand = t;
-    }
-    R.amax = __reduce_min_sync(FULL, cand);
-    const float avg = wsum(part_c) / p.fT;
+    for (int r = R - 1; r >= 0; --r)
+        if ((t0 + r) < T && cost[r] == maxc) cand = t0 + r;
+    Rw.amax = gmin_int<LPT>(cand, G.mask);
+    const float avg = gsum<LPT>(part_c, G.mask) / p.fT;
     toc = fmaf(p.lam_max, maxc, p.oml * avg);
 
     // start / goal rows
-    const int lT = (T - 1) & 31, rT = (T - 1) >> 5;
+    const int lT = (T - 1) / R, rT = (T - 1) % R;
     float qT[3] = {0.f, 0.f, 0.f}, vT[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-    for (int r = 0; r < RPL; ++r)
+    for (int r = 0; r < R; ++r)
         if (r == rT) {
 #pragma unroll
-            for (int b = 0; b < 3; ++b) { qT[b] = R.q[r][b]; vT[b] = R.v[r][b]; }
+            for (int b = 0; b < 3; ++b) { qT[b] = Rw.q[r][b]; vT[b] = Rw.v[r][b]; }
         }
 #pragma unroll
-    for (int b = 0; b < 3; ++b) { R.d0[b] = R.q[0][b] - start[b]; R.dT[b] = qT[b] - goal[b]; }
-    const float ssp0 = __shfl_sync(FULL, ss3(R.d0[0], R.d0[1], R.d0[2]), 0);
-    const float ssv0 = __shfl_sync(FULL, ss3(R.v[0][0], R.v[0][1], R.v[0][2]), 0);
-    const float sspT = __shfl_sync(FULL, ss3(R.dT[0], R.dT[1], R.dT[2]), lT);
-    const float ssvT = __shfl_sync(FULL, ss3(vT[0], vT[1], vT[2]), lT);
+    for (int b = 0; b < 3; ++b) { Rw.d0[b] = Rw.q[0][b] - start[b]; Rw.dT[b] = qT[b] - goal[b]; }
+    const float ssp0 = __shfl_sync(G.mask, ss3(Rw.d0[0], Rw.d0[1], Rw.d0[2]), G.base);
+    const float ssv0 = __shfl_sync(G.mask, ss3(Rw.v[0][0], Rw.v[0][1], Rw.v[0][2]), G.base);
+    const float sspT = __shfl_sync(G.mask, ss3(Rw.dT[0], Rw.dT[1], Rw.dT[2]), G.base + lT);
+    const float ssvT = __shfl_sync(G.mask, ss3(vT[0], vT[1], vT[2]), G.base + lT);
     const float sg = (0.5f * ssp0 + 0.5f * sspT) + (0.5f * ssv0 + 0.5f * ssvT);
-    const float jl = wsum(part_p) / p.fT + wsum(part_v) / p.fT;
+    const float jl = gsum<LPT>(part_p, G.mask) / p.fT + gsum<LPT>(part_v, G.mask) / p.fT;
     loss = fmaf(lam_jl, jl, fmaf(lam_sg, sg, toc));
     const bool ends_ok = (sqrtf(ssp0) < p.eps_pos) && (sqrtf(sspT) < p.eps_pos) &&
                          (sqrtf(ssv0) < p.eps_vel) && (sqrtf(ssvT) < p.eps_vel);
-    ful = (ends_ok && __all_sync(FULL, lim_ok)) ? 1 : 0;
+    ful = (ends_ok && gall<LPT>(lim_ok, G.mask)) ? 1 : 0;
 }
 
 // ---------------------------------------------------------------------------
@@ -262,20 +313,20 @@ __device__ __forceinline__ void cost_phase(const DevParams &p, const float2 *__r
 // written as the operands of the backward contraction: XA = G_q, XB = -G_v
 // (dK^T = -dK bit-exactly, checked in fgd_create()).
 // ---------------------------------------------------------------------------
-template <int RPL>
-__device__ __forceinline__ void grad_phase(const DevParams &p, int lane, const Rows<RPL> &R, float lam_sg, float lam_jl,
+template <int LPT, int R>
+__device__ __forceinline__ void grad_phase(const DevParams &p, const Group<LPT> &G, const Rows<R> &Rw, float lam_sg, float lam_jl,
                                            float4 *XA, float4 *XB)
 {
     const int T = p.T;
 #pragma unroll
-    for (int r = 0; r < RPL; ++r) {
-        const int t = lane + 32 * r;
+    for (int r = 0; r < R; ++r) {
+        const int t = G.gl * R + r;
         if (t >= T) continue;
-        const float wt = (t == R.amax) ? (p.lam_max + p.w_avg) : p.w_avg;
-        const float cgx = wt * R.gx[r], cgy = wt * R.gy[r];
+        const float wt = (t == Rw.amax) ? (p.lam_max + p.w_avg) : p.w_avg;
+        const float cgx = wt * Rw.gx[r], cgy = wt * Rw.gy[r];
         float xs[3], ys[3];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) { xs[k] = -(p.link[k] * R.sn[r][k]); ys[k] = p.link[k] * R.cs[r][k]; }
+        for (int k = 0; k < 3; ++k) { xs[k] = -(p.link[k] * Rw.sn[r][k]); ys[k] = p.link[k] * Rw.cs[r][k]; }
         const float Sx = (xs[0] + xs[1]) + xs[2], Sy = (ys[0] + ys[1]) + ys[2];
         const float Cx[3] = {xs[0], xs[0] + xs[1], (xs[0] + xs[1]) + xs[2]};
         const float Cy[3] = {ys[0], ys[0] + ys[1], (ys[0] + ys[1]) + ys[2]};
@@ -285,8 +336,8 @@ __device__ __forceinline__ void grad_phase(const DevParams &p, int lane, const R
             const float Jx = (xs[k] + Sx) - Cx[k];
             const float Jy = (ys[k] + Sy) - Cy[k];
             const float tg = fmaf(cgy, Jy, cgx * Jx);
-            const float qk = R.q[r][k], vk = R.v[r][k];
-            const float sgp = (t == 0) ? R.d0[k] : ((t == T - 1) ? R.dT[k] : 0.0f);
+            const float qk = Rw.q[r][k], vk = Rw.v[r][k];
+            const float sgp = (t == 0) ? Rw.d0[k] : ((t == T - 1) ? Rw.dT[k] : 0.0f);
             const float sgv = (t == 0 || t == T - 1) ? vk : 0.0f;
             const bool m = p.cvdl ? (qk > p.q_hi || qk < p.q_lo) : true;
             const float jpg = m ? ((qk - p.mean_q) * p.inv_std2) * p.inv_T : 0.0f;
@@ -301,12 +352,12 @@ __device__ __forceinline__ void grad_phase(const DevParams &p, int lane, const R
 }
 
 // alpha-gradient rows from the backward contraction: (K^T G_q + dK^T G_v) J^T
-template <int RPL>
-__device__ __forceinline__ void backward_rows(const DevParams &p, const float (&y1)[RPL][3], const float (&y2)[RPL][3],
-                                              float (&g)[RPL][3])
+template <int R>
+__device__ __forceinline__ void backward_rows(const DevParams &p, const float (&y1)[R][3], const float (&y2)[R][3],
+                                              float (&g)[R][3])
 {
 #pragma unroll
-    for (int r = 0; r < RPL; ++r) {
+    for (int r = 0; r < R; ++r) {
         const float r0 = y1[r][0] + y2[r][0], r1 = y1[r][1] + y2[r][1], r2 = y1[r][2] + y2[r][2];
 #pragma unroll
         for (int b = 0; b < 3; ++b) g[r][b] = fmaf(r2, p.J[b * 3 + 2], fmaf(r1, p.J[b * 3 + 1], r0 * p.J[b * 3]));

@@ -10,62 +10,62 @@ namespace fgd {
 struct SmemLayout {
     int k_floats;     // floats of staged K (and dK), 0 when K stays in L2
     int obs_pairs;    // obstacle slots (padded to even)
-    int x_rows;       // float4 rows per operand buffer (= T)
-    int n_slots;      // NW * S
+    int x_rows;       // float4 rows per operand buffer
+    int n_groups;     // trajectory groups per CTA
     __host__ __device__ size_t bytes() const
     {
-        return (size_t)2 * k_floats * 4 + (size_t)obs_pairs * 8 + (size_t)n_slots * 2 * x_rows * 16 + (size_t)n_slots * sizeof(Slot);
+        return (size_t)2 * k_floats * 4 + (size_t)obs_pairs * 8 + (size_t)n_groups * 2 * x_rows * 16 + (size_t)n_groups * sizeof(Slot);
     }
 };
 
-__host__ __device__ inline SmemLayout make_layout(int T, int TP, int n_obs, bool ks, int n_slots)
+__host__ __device__ inline SmemLayout make_layout(int T, int TP, int n_obs, bool ks, int n_groups)
 {
     SmemLayout l;
     l.k_floats = ks ? T * TP : 0;
     l.obs_pairs = (n_obs + 1) & ~1;
-    l.x_rows = T;
-    l.n_slots = n_slots;
+    l.x_rows = T | 1;     // odd row count: the operand buffers of neighbouring groups start 4 banks apart (mod 8)
+    l.n_groups = n_groups;
     return l;
 }
 
 __device__ __forceinline__ void hash_step(Slot &st, unsigned code) { st.hash = st.hash * 1000003u + code; }
 
 // candidate  (1 - lam_reg*lr) * alpha - lr * dir      optimizer_BLS.py:139, optimizer_GD.py:185
-template <int RPL>
-__device__ __forceinline__ void write_candidate(const DevParams &p, int lane, float lr, const float (&a)[RPL][3],
-                                                const float (&d)[RPL][3], float4 *XA)
+template <int LPT, int R>
+__device__ __forceinline__ void write_candidate(const DevParams &p, const Group<LPT> &G, float lr, const float (&a)[R][3],
+                                                const float (&d)[R][3], float4 *XA)
 {
     const float c1 = 1.0f - p.lam_reg * lr;
 #pragma unroll
-    for (int r = 0; r < RPL; ++r) {
-        const int t = lane + 32 * r;
+    for (int r = 0; r < R; ++r) {
+        const int t = G.gl * R + r;
         if (t < p.T)
             XA[t] = make_float4(fmaf(c1, a[r][0], -(lr * d[r][0])), fmaf(c1, a[r][1], -(lr * d[r][1])),
                                 fmaf(c1, a[r][2], -(lr * d[r][2])), 0.0f);
     }
 }
 
-template <int RPL>
-__device__ __forceinline__ void accept_candidate(const DevParams &p, float lr, float (&a)[RPL][3], const float (&d)[RPL][3])
+template <int R>
+__device__ __forceinline__ void accept_candidate(const DevParams &p, float lr, float (&a)[R][3], const float (&d)[R][3])
 {
     const float c1 = 1.0f - p.lam_reg * lr;
 #pragma unroll
-    for (int r = 0; r < RPL; ++r)
+    for (int r = 0; r < R; ++r)
 #pragma unroll
         for (int b = 0; b < 3; ++b) a[r][b] = fmaf(c1, a[r][b], -(lr * d[r][b]));
 }
 
-template <int RPL>
-__device__ __forceinline__ void save_slot(const DevParams &p, int lane, const Slot &st, int status, const float (&a)[RPL][3])
+template <int LPT, int R>
+__device__ __forceinline__ void save_slot(const DevParams &p, const Group<LPT> &G, const Slot &st, int status, const float (&a)[R][3])
 {
     const int b = st.traj;
     float *ap = p.alpha + (size_t)b * p.T * 3;
 #pragma unroll
-    for (int r = 0; r < RPL; ++r) {
-        const int t = lane + 32 * r;
+    for (int r = 0; r < R; ++r) {
+        const int t = G.gl * R + r;
         if (t < p.T) { ap[t * 3] = a[r][0]; ap[t * 3 + 1] = a[r][1]; ap[t * 3 + 2] = a[r][2]; }
     }
-    if (lane == 0) {
+    if (G.gl == 0) {
         float *fs = p.fstate + (size_t)b * FGD_FSTATE;
         int *is = p.istate + (size_t)b * FGD_ISTATE;
         fs[FGD_F_LAM_SG] = st.lam_sg; fs[FGD_F_LAM_JL] = st.lam_jl; fs[FGD_F_LR] = st.lr;
@@ -78,26 +78,27 @@ __device__ __forceinline__ void save_slot(const DevParams &p, int lane, const Sl
 
 // Start (or restart after a lambda increase / a resumed launch) with the loss and
 // gradient operands at the current alpha: optimizer_BLS.py:163, optimizer_GD.py:210.
-template <int RPL>
-__device__ __forceinline__ void begin_outer_eval(const DevParams &p, int lane, Slot &st, int &kind, const float (&a)[RPL][3], float4 *XA)
+template <int LPT, int R>
+__device__ __forceinline__ void begin_outer_eval(const DevParams &p, const Group<LPT> &G, Slot &st, int &kind, const float (&a)[R][3], float4 *XA)
 {
     if (p.mode == 1) st.lr = p.gd_lr[st.outer];
 #pragma unroll
-    for (int r = 0; r < RPL; ++r) {
-        const int t = lane + 32 * r;
+    for (int r = 0; r < R; ++r) {
+        const int t = G.gl * R + r;
         if (t < p.T) XA[t] = make_float4(a[r][0], a[r][1], a[r][2], 0.0f);
     }
     kind = K_EVAL0;
 }
 
-// Pull the next unfinished trajectory from the batch queue into this slot.
-template <int RPL>
-__device__ __forceinline__ void fetch_slot(const DevParams &p, int lane, Slot &st, int &kind, float (&a)[RPL][3], float4 *XA)
+// Pull the next unfinished trajectory from the batch queue into this group.
+// Called with the lanes of ONE group converged (possibly diverged from the rest of the warp).
+template <int LPT, int R>
+__device__ __forceinline__ void fetch_slot(const DevParams &p, const Group<LPT> &G, Slot &st, int &kind, float (&a)[R][3], float4 *XA)
 {
     for (;;) {
         unsigned idx = 0;
-        if (lane == 0) idx = atomicAdd(p.queue, 1u);
-        idx = __shfl_sync(FULL, idx, 0);
+        if (G.gl == 0) idx = atomicAdd(p.queue, 1u);
+        idx = __shfl_sync(G.mask, idx, G.base);
         if (idx >= (unsigned)p.B) { st.traj = -1; kind = K_IDLE; return; }
         const int *is = p.istate + (size_t)idx * FGD_ISTATE;
         const int status = is[FGD_I_STATUS];
@@ -121,20 +122,20 @@ __device__ __forceinline__ void fetch_slot(const DevParams &p, int lane, Slot &s
         for (int b = 0; b < 3; ++b) { st.start[b] = p.start[(size_t)idx * 3 + b]; st.goal[b] = p.goal[(size_t)idx * 3 + b]; }
         const float *ap = p.alpha + (size_t)idx * p.T * 3;
 #pragma unroll
-        for (int r = 0; r < RPL; ++r) {
-            const int t = lane + 32 * r;
+        for (int r = 0; r < R; ++r) {
+            const int t = G.gl * R + r;
             const bool ok = t < p.T;
             a[r][0] = ok ? ap[t * 3] : 0.0f; a[r][1] = ok ? ap[t * 3 + 1] : 0.0f; a[r][2] = ok ? ap[t * 3 + 2] : 0.0f;
         }
-        begin_outer_eval<RPL>(p, lane, st, kind, a, XA);
+        begin_outer_eval<LPT, R>(p, G, st, kind, a, XA);
         return;
     }
 }
 
 // End of an inner loop: constraint verdict, lambda escalation, next outer
 // iteration or retirement.   optimizer_BLS.py:196-205, optimizer_GD.py:214-224
-template <int RPL>
-__device__ __forceinline__ void end_inner(const DevParams &p, int lane, Slot &st, int &kind, float (&a)[RPL][3], float4 *XA)
+template <int LPT, int R>
+__device__ __forceinline__ void end_inner(const DevParams &p, const Group<LPT> &G, Slot &st, int &kind, float (&a)[R][3], float4 *XA)
 {
     const bool dual = (p.mode == 0) || (p.max_outer > 1);
     bool retire = !dual || st.ful;
@@ -144,262 +145,269 @@ __device__ __forceinline__ void end_inner(const DevParams &p, int lane, Slot &st
         retire = st.outer >= p.max_outer;
     }
     if (retire) {
-        save_slot<RPL>(p, lane, st, FGD_ST_DONE, a);
-        fetch_slot<RPL>(p, lane, st, kind, a, XA);
+        save_slot<LPT, R>(p, G, st, FGD_ST_DONE, a);
+        fetch_slot<LPT, R>(p, G, st, kind, a, XA);
         return;
     }
     st.inner = 0;
     if (p.mode == 0) st.lr = p.bls_lr0;       // optimizer_BLS.py:193
-    begin_outer_eval<RPL>(p, lane, st, kind, a, XA);
+    begin_outer_eval<LPT, R>(p, G, st, kind, a, XA);
 }
 
 // Head of the inner loop (optimizer_BLS.py:155-157): continue with a gradient,
 // stop at the launch budget, or fall through to the constraint check.
-template <int RPL>
-__device__ __forceinline__ void inner_head(const DevParams &p, int lane, Slot &st, int &kind, float (&a)[RPL][3], float4 *XA)
+template <int LPT, int R>
+__device__ __forceinline__ void inner_head(const DevParams &p, const Group<LPT> &G, Slot &st, int &kind, float (&a)[R][3], float4 *XA)
 {
     if (st.inner < p.max_inner) {
         if (p.budget >= 0 && st.done_iters == p.budget) {
-            save_slot<RPL>(p, lane, st, FGD_ST_ACTIVE, a);
-            fetch_slot<RPL>(p, lane, st, kind, a, XA);
+            save_slot<LPT, R>(p, G, st, FGD_ST_ACTIVE, a);
+            fetch_slot<LPT, R>(p, G, st, kind, a, XA);
             return;
         }
         st.done_iters += 1; st.inner_total += 1;
         kind = K_BACK;
         return;
     }
-    end_inner<RPL>(p, lane, st, kind, a, XA);
+    end_inner<LPT, R>(p, G, st, kind, a, XA);
+}
+
+template <bool KS>
+__device__ __forceinline__ void stage_constants(const DevParams &p, const SmemLayout &L, float *sK, float *sdK, float2 *sObs, int nthreads)
+{
+    if constexpr (KS) {
+        const float4 *gK = reinterpret_cast<const float4 *>(p.Kt), *gD = reinterpret_cast<const float4 *>(p.dKt);
+        float4 *dK4 = reinterpret_cast<float4 *>(sK), *dD4 = reinterpret_cast<float4 *>(sdK);
+        for (int i = threadIdx.x; i < L.k_floats / 4; i += nthreads) { dK4[i] = __ldg(gK + i); dD4[i] = __ldg(gD + i); }
+    }
+    for (int i = threadIdx.x; i < p.n_obs; i += nthreads) sObs[i] = make_float2(p.obs[2 * i], p.obs[2 * i + 1]);
+    __syncthreads();
 }
 
 // ---------------------------------------------------------------------------
-// Persistent optimiser: every warp owns S slots and keeps pulling trajectories
-// until the batch queue is empty.  One loop trip = one contraction for every
-// slot + the slot's post-processing (candidate evaluation or gradient).
+// Persistent optimiser: every group of LPT lanes runs one trajectory as an
+// autonomous state machine and keeps pulling trajectories until the batch queue
+// is empty.  One loop trip = one contraction (K loads shared by the groups of
+// the warp) + the group's post-processing (candidate evaluation or gradient).
 // ---------------------------------------------------------------------------
-template <int RPL, int S, bool STRICT, bool KS, int NW>
-__global__ void __launch_bounds__(NW * 32) fgd_optimize_kernel(const __grid_constant__ DevParams p)
+template <int LPT, int R, bool STRICT, bool KS, int NW, int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __grid_constant__ DevParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int GPW = 32 / LPT;                    // groups (trajectories) per warp
     const int T = p.T, TP = p.TP;
-    const SmemLayout L = make_layout(T, TP, p.n_obs, KS, NW * S);
+    const SmemLayout L = make_layout(T, TP, p.n_obs, KS, NW * GPW);
     float *sK = reinterpret_cast<float *>(smem_raw);
     float *sdK = sK + L.k_floats;
     float2 *sObs = reinterpret_cast<float2 *>(sdK + L.k_floats);
     float4 *sX = reinterpret_cast<float4 *>(sObs + L.obs_pairs);
-    Slot *sSlot = reinterpret_cast<Slot *>(sX + (size_t)L.n_slots * 2 * L.x_rows);
+    Slot *sSlot = reinterpret_cast<Slot *>(sX + (size_t)L.n_groups * 2 * L.x_rows);
+    stage_constants<KS>(p, L, sK, sdK, sObs, NW * 32);
 
-    if constexpr (KS) {
-        const float4 *gK = reinterpret_cast<const float4 *>(p.Kt), *gD = reinterpret_cast<const float4 *>(p.dKt);
-        float4 *dK4 = reinterpret_cast<float4 *>(sK), *dD4 = reinterpret_cast<float4 *>(sdK);
-        for (int i = threadIdx.x; i < L.k_floats / 4; i += NW * 32) { dK4[i] = __ldg(gK + i); dD4[i] = __ldg(gD + i); }
-    }
-    for (int i = threadIdx.x; i < p.n_obs; i += NW * 32) sObs[i] = make_float2(p.obs[2 * i], p.obs[2 * i + 1]);
-    __syncthreads();
+    const Group<LPT> G;
+    const int warp = threadIdx.x >> 5;
+    const int gidx = warp * GPW + (G.lane / LPT);
+    const float *kp = (KS ? sK : p.Kt) + G.gl * R, *dp = (KS ? sdK : p.dKt) + G.gl * R;
+    float4 *XA = sX + (size_t)(gidx * 2) * L.x_rows, *XB = XA + L.x_rows;
+    Slot *slot = sSlot + gidx;
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const float *Kt = KS ? sK : p.Kt, *dKt = KS ? sdK : p.dKt;
-
-    float4 *XA[S], *XB[S];
-    Slot *slot[S];
-    int kind[S];
-    float a[S][RPL][3];     // alpha rows of this lane
-    float d[S][RPL][3];     // step direction rows (normalised gradient for BLS, gradient for GD)
+    int kind = K_IDLE;
+    float a[R][3];     // alpha rows of this lane
+    float d[R][3];     // step direction rows (normalised gradient for BLS, gradient for GD)
 #pragma unroll
-    for (int s = 0; s < S; ++s) {
-        const int gs = warp * S + s;
-        XA[s] = sX + (size_t)(gs * 2) * L.x_rows;
-        XB[s] = XA[s] + L.x_rows;
-        slot[s] = sSlot + gs;
-        kind[s] = K_IDLE;
+    for (int r = 0; r < R; ++r)
 #pragma unroll
-        for (int r = 0; r < RPL; ++r)
-#pragma unroll
-            for (int b = 0; b < 3; ++b) { a[s][r][b] = 0.0f; d[s][r][b] = 0.0f; }
+        for (int b = 0; b < 3; ++b) { a[r][b] = 0.0f; d[r][b] = 0.0f; }
+    {
         Slot st;
-        fetch_slot<RPL>(p, lane, st, kind[s], a[s], XA[s]);
-        *slot[s] = st;
+        fetch_slot<LPT, R>(p, G, st, kind, a, XA);
+        *slot = st;
     }
 
     for (;;) {
-        bool any = false;
-#pragma unroll
-        for (int s = 0; s < S; ++s) any |= (kind[s] != K_IDLE);
-        if (!any) break;
-
-        const float4 *x1[S], *x2[S];
-#pragma unroll
-        for (int s = 0; s < S; ++s) { x1[s] = XA[s]; x2[s] = (kind[s] == K_BACK) ? XB[s] : XA[s]; }
-        float y1[S][RPL][3], y2[S][RPL][3];
+        if (!__any_sync(FULL, kind != K_IDLE)) break;
+        const float4 *x1 = XA, *x2 = (kind == K_BACK) ? XB : XA;
+        float y1[R][3], y2[R][3];
         __syncwarp();
-        contract<RPL, S, KS>(Kt, dKt, T, TP, lane, x1, x2, y1, y2);
+        contract<R, KS>(kp, dp, T, TP, x1, x2, y1, y2);
         __syncwarp();
-
+        if (kind != K_IDLE) {
+        // group-uniform scalars: every lane works on its own register copy and all lanes of the
+        // group write back identical values (race-free by construction)
+        Slot st = *slot;
+        __syncwarp(G.mask);
+        if (kind == K_BACK) {
+            // ---- alpha-gradient, normalisation, first candidate ----------------
+            float g[R][3];
+            backward_rows<R>(p, y1, y2, g);
+            if (p.mode == 0) {
+                float part = 0.0f;
 #pragma unroll
-        for (int s = 0; s < S; ++s) {
-            if (kind[s] == K_IDLE) continue;
-            // warp-uniform scalars: every lane works on its own register copy and
-            // all lanes write back identical values (race-free by construction)
-            Slot st = *slot[s];
-            __syncwarp();
-            if (kind[s] == K_BACK) {
-                // ---- alpha-gradient, normalisation, first candidate ----------
-                float g[RPL][3];
-                backward_rows<RPL>(p, y1[s], y2[s], g);
-                if (p.mode == 0) {
-                    float part = 0.0f;
+                for (int r = 0; r < R; ++r)
+                    if (G.gl * R + r < T) part = part + ss3(g[r][0], g[r][1], g[r][2]);
+                const float nrm = sqrtf(gsum<LPT>(part, G.mask));                  // optimizer_BLS.py:165
+                float pb = 0.0f;
 #pragma unroll
-                    for (int r = 0; r < RPL; ++r)
-                        if (lane + 32 * r < T) part = part + ss3(g[r][0], g[r][1], g[r][2]);
-                    const float nrm = sqrtf(wsum(part));                  // optimizer_BLS.py:165
-                    float pb = 0.0f;
+                for (int r = 0; r < R; ++r) {
 #pragma unroll
-                    for (int r = 0; r < RPL; ++r) {
-#pragma unroll
-                        for (int b = 0; b < 3; ++b) d[s][r][b] = g[r][b] / nrm;
-                        if (lane + 32 * r < T)
-                            pb = pb + ((g[r][0] + g[r][1]) + g[r][2]) * ((d[s][r][0] + d[s][r][1]) + d[s][r][2]);
-                    }
-                    st.alpha_norm = wsum(pb);                             // optimizer_BLS.py:166
-                    st.j = 0;
-                } else {
-#pragma unroll
-                    for (int r = 0; r < RPL; ++r)
-#pragma unroll
-                        for (int b = 0; b < 3; ++b) d[s][r][b] = g[r][b];
+                    for (int b = 0; b < 3; ++b) d[r][b] = g[r][b] / nrm;
+                    if (G.gl * R + r < T)
+                        pb = pb + ((g[r][0] + g[r][1]) + g[r][2]) * ((d[r][0] + d[r][1]) + d[r][2]);
                 }
-                write_candidate<RPL>(p, lane, st.lr, a[s], d[s], XA[s]);
-                kind[s] = K_CAND;
+                st.alpha_norm = gsum<LPT>(pb, G.mask);                             // optimizer_BLS.py:166
+                st.j = 0;
             } else {
-                // ---- loss (and, if needed, gradient operands) at alpha or at a candidate
-                Rows<RPL> R;
-                float loss_c, toc_c;
-                int ful_c;
-                cost_phase<RPL, STRICT>(p, sObs, lane, y1[s], y2[s], st.start, st.goal, st.lam_sg, st.lam_jl, R, loss_c, toc_c, ful_c);
-                if (kind[s] == K_EVAL0) {
-                    st.loss = loss_c; st.toc = toc_c; st.ful = ful_c;
-                    grad_phase<RPL>(p, lane, R, st.lam_sg, st.lam_jl, XA[s], XB[s]);
-                    inner_head<RPL>(p, lane, st, kind[s], a[s], XA[s]);
-                } else if (p.mode == 0) {
-                    // Armijo test   optimizer_BLS.py:141-149
-                    st.cand_evals += 1;
-                    const float lr = st.lr, loss = st.loss;
-                    const float req = loss - (p.bls_alpha * lr) * st.alpha_norm;
-                    if (loss_c > req) {
-                        st.lr = lr * p.bls_bm; hash_step(st, 1u);
-                        st.j += 1;
-                        if (st.j < p.max_bls) {
-                            write_candidate<RPL>(p, lane, st.lr, a[s], d[s], XA[s]);
-                        } else {
-                            // every candidate rejected: new_loss := loss (optimizer_BLS.py:170,178)
-                            st.last_new = loss;
-                            const bool minimized = (loss - loss < p.eps_loop);
-                            if (minimized) { hash_step(st, 3u); end_inner<RPL>(p, lane, st, kind[s], a[s], XA[s]); }
-                            else { st.inner += 1; begin_outer_eval<RPL>(p, lane, st, kind[s], a[s], XA[s]); }
-                        }
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+#pragma unroll
+                    for (int b = 0; b < 3; ++b) d[r][b] = g[r][b];
+            }
+            write_candidate<LPT, R>(p, G, st.lr, a, d, XA);
+            kind = K_CAND;
+        } else {
+            // ---- loss (and, if accepted, gradient operands) at alpha or at a candidate
+            Rows<R> Rw;
+            float loss_c, toc_c;
+            int ful_c;
+            cost_phase<LPT, R, STRICT>(p, sObs, G, y1, y2, st.start, st.goal, st.lam_sg, st.lam_jl, Rw, loss_c, toc_c, ful_c);
+            if (kind == K_EVAL0) {
+                st.loss = loss_c; st.toc = toc_c; st.ful = ful_c;
+                grad_phase<LPT, R>(p, G, Rw, st.lam_sg, st.lam_jl, XA, XB);
+                inner_head<LPT, R>(p, G, st, kind, a, XA);
+            } else if (p.mode == 0) {
+                // Armijo test   optimizer_BLS.py:141-149
+                st.cand_evals += 1;
+                const float lr = st.lr, loss = st.loss;
+                const float req = loss - (p.bls_alpha * lr) * st.alpha_norm;
+                if (loss_c > req) {
+                    st.lr = lr * p.bls_bm; hash_step(st, 1u);
+                    st.j += 1;
+                    if (st.j < p.max_bls) {
+                        write_candidate<LPT, R>(p, G, st.lr, a, d, XA);
                     } else {
-                        accept_candidate<RPL>(p, lr, a[s], d[s]);
-                        grad_phase<RPL>(p, lane, R, st.lam_sg, st.lam_jl, XA[s], XB[s]);
-                        st.lr = lr * p.bls_bp; st.accepts += 1; hash_step(st, 2u);
-                        st.ful = ful_c; st.toc = toc_c; st.last_new = loss_c;
-                        const bool minimized = (loss - loss_c < p.eps_loop);     // optimizer_BLS.py:178
-                        st.loss = loss_c;
-                        if (minimized) { hash_step(st, 3u); end_inner<RPL>(p, lane, st, kind[s], a[s], XA[s]); }
-                        else { st.inner += 1; inner_head<RPL>(p, lane, st, kind[s], a[s], XA[s]); }
+                        // every candidate rejected: new_loss := loss (optimizer_BLS.py:170,178)
+                        st.last_new = loss;
+                        const bool minimized = (loss - loss < p.eps_loop);
+                        if (minimized) { hash_step(st, 3u); end_inner<LPT, R>(p, G, st, kind, a, XA); }
+                        else { st.inner += 1; begin_outer_eval<LPT, R>(p, G, st, kind, a, XA); }
                     }
                 } else {
-                    // fixed-step GD   optimizer_GD.py:186-194
-                    st.cand_evals += 1;
-                    st.last_new = loss_c;
-                    if (st.loss - loss_c < p.eps_loop) {
-                        hash_step(st, 3u);
-                        end_inner<RPL>(p, lane, st, kind[s], a[s], XA[s]);
-                    } else {
-                        accept_candidate<RPL>(p, st.lr, a[s], d[s]);
-                        grad_phase<RPL>(p, lane, R, st.lam_sg, st.lam_jl, XA[s], XB[s]);
-                        st.loss = loss_c; st.ful = ful_c; st.toc = toc_c;
-                        st.accepts += 1; st.inner += 1; hash_step(st, 2u);
-                        inner_head<RPL>(p, lane, st, kind[s], a[s], XA[s]);
-                    }
+                    accept_candidate<R>(p, lr, a, d);
+                    grad_phase<LPT, R>(p, G, Rw, st.lam_sg, st.lam_jl, XA, XB);
+                    st.lr = lr * p.bls_bp; st.accepts += 1; hash_step(st, 2u);
+                    st.ful = ful_c; st.toc = toc_c; st.last_new = loss_c;
+                    const bool minimized = (loss - loss_c < p.eps_loop);           // optimizer_BLS.py:178
+                    st.loss = loss_c;
+                    if (minimized) { hash_step(st, 3u); end_inner<LPT, R>(p, G, st, kind, a, XA); }
+                    else { st.inner += 1; inner_head<LPT, R>(p, G, st, kind, a, XA); }
+                }
+            } else {
+                // fixed-step GD   optimizer_GD.py:186-194
+                st.cand_evals += 1;
+                st.last_new = loss_c;
+                if (st.loss - loss_c < p.eps_loop) {
+                    hash_step(st, 3u);
+                    end_inner<LPT, R>(p, G, st, kind, a, XA);
+                } else {
+                    accept_candidate<R>(p, st.lr, a, d);
+                    grad_phase<LPT, R>(p, G, Rw, st.lam_sg, st.lam_jl, XA, XB);
+                    st.loss = loss_c; st.ful = ful_c; st.toc = toc_c;
+                    st.accepts += 1; st.inner += 1; hash_step(st, 2u);
+                    inner_head<LPT, R>(p, G, st, kind, a, XA);
                 }
             }
-            *slot[s] = st;
+        }
+        *slot = st;
         }
     }
 }
 
 // ---------------------------------------------------------------------------
 // Evaluation only (unit-parity hook and the host's compute_trajectory_cost*):
-// one warp per trajectory, grid-stride.
+// one group per trajectory, grid-stride.
 // ---------------------------------------------------------------------------
-template <int RPL, bool STRICT, bool KS, int NW>
+template <int LPT, int R, bool STRICT, bool KS, int NW>
 __global__ void __launch_bounds__(NW * 32) fgd_eval_kernel(const __grid_constant__ DevParams p, const EvalPtrs e)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int GPW = 32 / LPT;
     const int T = p.T, TP = p.TP;
-    const SmemLayout L = make_layout(T, TP, p.n_obs, KS, NW);
+    const SmemLayout L = make_layout(T, TP, p.n_obs, KS, NW * GPW);
     float *sK = reinterpret_cast<float *>(smem_raw);
     float *sdK = sK + L.k_floats;
     float2 *sObs = reinterpret_cast<float2 *>(sdK + L.k_floats);
     float4 *sX = reinterpret_cast<float4 *>(sObs + L.obs_pairs);
-    if constexpr (KS) {
-        const float4 *gK = reinterpret_cast<const float4 *>(p.Kt), *gD = reinterpret_cast<const float4 *>(p.dKt);
-        float4 *dK4 = reinterpret_cast<float4 *>(sK), *dD4 = reinterpret_cast<float4 *>(sdK);
-        for (int i = threadIdx.x; i < L.k_floats / 4; i += NW * 32) { dK4[i] = __ldg(gK + i); dD4[i] = __ldg(gD + i); }
-    }
-    for (int i = threadIdx.x; i < p.n_obs; i += NW * 32) sObs[i] = make_float2(p.obs[2 * i], p.obs[2 * i + 1]);
-    __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const float *Kt = KS ? sK : p.Kt, *dKt = KS ? sdK : p.dKt;
-    float4 *XA = sX + (size_t)(warp * 2) * L.x_rows, *XB = XA + L.x_rows;
+    stage_constants<KS>(p, L, sK, sdK, sObs, NW * 32);
 
-    for (int b = blockIdx.x * NW + warp; b < p.B; b += gridDim.x * NW) {
-        const float *ap = p.alpha + (size_t)b * T * 3;
+    const Group<LPT> G;
+    const int warp = threadIdx.x >> 5;
+    const int gidx = warp * GPW + (G.lane / LPT);
+    const float *kp = (KS ? sK : p.Kt) + G.gl * R, *dp = (KS ? sdK : p.dKt) + G.gl * R;
+    float4 *XA = sX + (size_t)(gidx * 2) * L.x_rows, *XB = XA + L.x_rows;
+    const int stride = gridDim.x * NW * GPW;
+    const int n_rounds = (p.B + stride - 1) / stride;
+
+    // operand buffers start defined (dead groups contract whatever is there and write nothing)
 #pragma unroll
-        for (int r = 0; r < RPL; ++r) {
-            const int t = lane + 32 * r;
-            if (t < T) XA[t] = make_float4(ap[t * 3], ap[t * 3 + 1], ap[t * 3 + 2], 0.0f);
-        }
-        float start[3], goal[3];
+    for (int r = 0; r < R; ++r) {
+        const int t = G.gl * R + r;
+        if (t < T) { XA[t] = make_float4(0.f, 0.f, 0.f, 0.f); XB[t] = make_float4(0.f, 0.f, 0.f, 0.f); }
+    }
+
+    for (int round = 0; round < n_rounds; ++round) {
+        const int b = round * stride + blockIdx.x * NW * GPW + gidx;
+        const bool live = b < p.B;
+        float start[3] = {0.f, 0.f, 0.f}, goal[3] = {0.f, 0.f, 0.f};
+        if (live) {
+            const float *ap = p.alpha + (size_t)b * T * 3;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) { start[k] = p.start[(size_t)b * 3 + k]; goal[k] = p.goal[(size_t)b * 3 + k]; }
-        const float4 *x1[1] = {XA}, *x2[1] = {XA};
-        float y1[1][RPL][3], y2[1][RPL][3];
-        __syncwarp();
-        contract<RPL, 1, KS>(Kt, dKt, T, TP, lane, x1, x2, y1, y2);
-        __syncwarp();
-        Rows<RPL> R;
-        float loss, toc;
-        int ful;
-        cost_phase<RPL, STRICT>(p, sObs, lane, y1[0], y2[0], start, goal, e.lam_sg, e.lam_jl, R, loss, toc, ful);
-        if (lane == 0) {
-            if (e.loss) e.loss[b] = loss;
-            if (e.toc) e.toc[b] = toc;
-            if (e.fulfilled) e.fulfilled[b] = ful;
-        }
-#pragma unroll
-        for (int r = 0; r < RPL; ++r) {
-            const int t = lane + 32 * r;
-            if (t < T) {
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    if (e.q) e.q[((size_t)b * T + t) * 3 + k] = R.q[r][k];
-                    if (e.v) e.v[((size_t)b * T + t) * 3 + k] = R.v[r][k];
-                }
+            for (int r = 0; r < R; ++r) {
+                const int t = G.gl * R + r;
+                if (t < T) XA[t] = make_float4(ap[t * 3], ap[t * 3 + 1], ap[t * 3 + 2], 0.0f);
             }
-        }
-        if (e.grad) {
-            grad_phase<RPL>(p, lane, R, e.lam_sg, e.lam_jl, XA, XB);
-            const float4 *g1[1] = {XA}, *g2[1] = {XB};
-            __syncwarp();
-            contract<RPL, 1, KS>(Kt, dKt, T, TP, lane, g1, g2, y1, y2);
-            float g[RPL][3];
-            backward_rows<RPL>(p, y1[0], y2[0], g);
 #pragma unroll
-            for (int r = 0; r < RPL; ++r) {
-                const int t = lane + 32 * r;
+            for (int k = 0; k < 3; ++k) { start[k] = p.start[(size_t)b * 3 + k]; goal[k] = p.goal[(size_t)b * 3 + k]; }
+        }
+        float y1[R][3], y2[R][3];
+        __syncwarp();
+        contract<R, KS>(kp, dp, T, TP, XA, XA, y1, y2);
+        __syncwarp();
+        if (live) {
+            Rows<R> Rw;
+            float loss, toc;
+            int ful;
+            cost_phase<LPT, R, STRICT>(p, sObs, G, y1, y2, start, goal, e.lam_sg, e.lam_jl, Rw, loss, toc, ful);
+            if (G.gl == 0) {
+                if (e.loss) e.loss[b] = loss;
+                if (e.toc) e.toc[b] = toc;
+                if (e.fulfilled) e.fulfilled[b] = ful;
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int t = G.gl * R + r;
                 if (t < T) {
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) e.grad[((size_t)b * T + t) * 3 + k] = g[r][k];
+                    for (int k = 0; k < 3; ++k) {
+                        if (e.q) e.q[((size_t)b * T + t) * 3 + k] = Rw.q[r][k];
+                        if (e.v) e.v[((size_t)b * T + t) * 3 + k] = Rw.v[r][k];
+                    }
+                }
+            }
+            if (e.grad) grad_phase<LPT, R>(p, G, Rw, e.lam_sg, e.lam_jl, XA, XB);
+        }
+        if (e.grad) {
+            __syncwarp();
+            contract<R, KS>(kp, dp, T, TP, XA, XB, y1, y2);
+            if (live) {
+                float g[R][3];
+                backward_rows<R>(p, y1, y2, g);
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int t = G.gl * R + r;
+                    if (t < T) {
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) e.grad[((size_t)b * T + t) * 3 + k] = g[r][k];
+                    }
                 }
             }
         }

@@ -22,8 +22,9 @@
  *
  * Deliberate, documented re-associations w.r.t. the NumPy restatement (all
  * within 1-2 ulp per operation; tolerances in tests/test_oracle_mirror.py):
- *   - 0.8/den is computed as 0.8f * (1.0f/den); the obstacle gradient uses
- *     -(c*r)*d instead of (-0.8*d)/den^2           (environment.py:43,57)
+ *   - the obstacle term accumulates sum_o 1/den and sum_o d/den^2 (reciprocal, not
+ *     division) and applies the factors 0.8 / -0.8 once per time sample
+ *                                                  (environment.py:43,57)
  *   - (q-mean)/std, /std^2, v/vmax, /T in the limit penalties multiply by
  *     host-rounded reciprocals                     (trajectory.py:217,232,247,260)
  *   - alpha_norm = sum_t (sum_a g[t,a]) * (sum_b n[t,b]), algebraically equal
@@ -107,20 +108,31 @@ static void mirror_sincos(float x, float *s_out, float *c_out)
 }
 
 /* ---- fixed-order reductions -------------------------------------------- */
-/* lane L owns rows t = L, L+32, L+64, ...; lane partial = sequential sum over
- * its rows (from +0), then a 5-level xor butterfly 16,8,4,2,1.              */
+/* A trajectory is owned by LPT lanes; lane l owns the R adjacent rows t = R*l .. R*l+R-1
+ * (LPT*R >= T).  Sum over t: lane partial = sequential sum over its rows (from +0), then an
+ * xor butterfly LPT/2, ..., 2, 1 over the lanes.  Same mapping table as the CUDA side.   */
+static void mapping_for(int T, int *LPT, int *R)
+{
+    if (T <= 32) { *LPT = 8; *R = 4; }
+    else if (T <= 64) { *LPT = 16; *R = 4; }
+    else if (T <= 128) { *LPT = 32; *R = 4; }
+    else { *LPT = 32; *R = 8; }
+}
+
 static float tree_sum(const float *x, int T)
 {
+    int LPT, R;
+    mapping_for(T, &LPT, &R);
     float p[32];
-    for (int L = 0; L < 32; ++L) {
+    for (int l = 0; l < LPT; ++l) {
         float a = 0.0f;
-        for (int t = L; t < T; t += 32) a = a + x[t];
-        p[L] = a;
+        for (int r = 0; r < R; ++r) { const int t = R * l + r; if (t < T) a = a + x[t]; }
+        p[l] = a;
     }
-    for (int off = 16; off >= 1; off >>= 1) {
+    for (int off = LPT / 2; off >= 1; off >>= 1) {
         float q[32];
-        for (int L = 0; L < 32; ++L) q[L] = p[L] + p[L ^ off];
-        memcpy(p, q, sizeof p);
+        for (int l = 0; l < LPT; ++l) q[l] = p[l] + p[l ^ off];
+        memcpy(p, q, sizeof(float) * LPT);
     }
     return p[0];
 }
@@ -176,19 +188,18 @@ static void evaluate_point(const MirrorCfg *c, const Derived *d, const float *K,
         mirror_sincos(c3, &sn[t][2], &cs[t][2]);
         float x = fmaf(c->link[2], cs[t][2], fmaf(c->link[1], cs[t][1], c->link[0] * cs[t][0]));  /* robot.py:33 */
         float y = fmaf(c->link[2], sn[t][2], fmaf(c->link[1], sn[t][1], c->link[0] * sn[t][0]));  /* robot.py:34 */
-        float cost = 0.0f, ax = 0.0f, ay = 0.0f;
+        float sr = 0.0f, sx = 0.0f, sy = 0.0f;
         for (int o = 0; o < c->n_obs; ++o) {                 /* environment.py:46-58 */
             float dx = x - obs[2 * o], dy = y - obs[2 * o + 1];
             float n = fmaf(dy, dy, dx * dx);
             float den = fmaf(0.5f, n, 0.5f);
             float r = 1.0f / den;
-            float cc = 0.8f * r;
-            cost = cost + cc;
-            float w = -(cc * r);
-            ax = fmaf(w, dx, ax);
-            ay = fmaf(w, dy, ay);
+            sr = sr + r;                                     /* sum 1/den            */
+            float r2 = r * r;
+            sx = fmaf(r2, dx, sx);                           /* sum d/den^2          */
+            sy = fmaf(r2, dy, sy);
         }
-        costv[t] = cost; gx[t] = ax; gy[t] = ay;
+        costv[t] = 0.8f * sr; gx[t] = -0.8f * sx; gy[t] = -0.8f * sy;
         /* joint-limit penalties  trajectory.py:215-268 */
         float ep = 0.0f, ev = 0.0f;
         float e3[3], f3[3];

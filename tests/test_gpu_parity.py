@@ -21,18 +21,13 @@ from oracle import mirror as M
 pytestmark = pytest.mark.gpu
 
 
-def _setup(T=50, n_obs=11, seed=0, B=64, strict=True, slots=None, capacity=1024, **over):
+def _setup(T=50, n_obs=11, seed=0, B=64, strict=True, capacity=1024, **over):
     import torch
     from irm_motion_planning_b200.environment import Environment, random_obstacles
     from irm_motion_planning_b200.trajectory import Trajectory
     from irm_motion_planning_b200.workloads import default_args, sample_start_goal
-    if slots is None:
-        os.environ.pop("FGD_TRAJ_PER_WARP", None)
-    else:
-        os.environ["FGD_TRAJ_PER_WARP"] = str(slots)
     args = default_args(n_timesteps=float(T), **over)
     tr = Trajectory(args, obstacle_capacity=capacity, strict_math=strict)
-    os.environ.pop("FGD_TRAJ_PER_WARP", None)
     rng = np.random.default_rng(seed)
     obs = Environment().obstacles if n_obs == 11 else random_obstacles(n_obs, rng)
     start, goal = sample_start_goal(B, rng)
@@ -65,7 +60,7 @@ def _gpu_optimize(tr, mode, alpha0, start, goal, budget=-1, state=None):
     return a, fs, is_
 
 
-@pytest.mark.parametrize("T,n_obs", [(50, 11), (20, 11), (33, 37), (64, 5), (100, 64), (256, 300)])
+@pytest.mark.parametrize("T,n_obs", [(50, 11), (20, 11), (33, 37), (64, 5), (65, 9), (100, 64), (129, 20), (256, 300)])
 def test_eval_bit_exact_strict(cuda_ready, T, n_obs):
     args, tr, obs, start, goal, alpha0 = _setup(T=T, n_obs=n_obs, B=24, seed=T)
     rng = np.random.default_rng(T + 1)
@@ -107,21 +102,22 @@ def test_eval_lambda_max_override(cuda_ready):
         assert np.array_equal(g["loss"], c["loss"])
 
 
-@pytest.mark.parametrize("mode,slots,T,n_obs,B,over", [
-    ("bls", 1, 50, 11, 200, {}),
+@pytest.mark.parametrize("mode,gpw,T,n_obs,B,over", [
     ("bls", 2, 50, 11, 200, {}),
-    ("bls", 4, 50, 11, 333, {}),
-    ("gd", 4, 50, 11, 200, {"max_outer_iteration": 1}),
+    ("bls", 2, 50, 11, 333, {}),
+    ("bls", 2, 64, 11, 61, {}),
+    ("gd", 2, 50, 11, 200, {"max_outer_iteration": 1}),
     ("gd", 2, 50, 11, 96, {}),
     ("bls", 4, 24, 30, 100, {}),
-    ("bls", 2, 100, 40, 48, {"max_inner_iteration": 40, "max_outer_iteration": 3}),
+    ("bls", 4, 7, 3, 37, {}),
+    ("bls", 1, 100, 40, 48, {"max_inner_iteration": 40, "max_outer_iteration": 3}),
     ("bls", 1, 256, 200, 16, {"max_inner_iteration": 12, "max_outer_iteration": 2}),
-    ("bls", 4, 50, 11, 64, {"constraint_violating_dependant_loss": False, "lambda_max_cost": 0.25}),
+    ("bls", 2, 50, 11, 64, {"constraint_violating_dependant_loss": False, "lambda_max_cost": 0.25}),
 ])
-def test_optimize_bit_exact_strict(cuda_ready, mode, slots, T, n_obs, B, over):
+def test_optimize_bit_exact_strict(cuda_ready, mode, gpw, T, n_obs, B, over):
     """Whole optimisation (all outer / inner / line-search iterations) bit-identical to the oracle:
     final alpha, penalty weights, step size, loss, counters and decision hash of every trajectory."""
-    args, tr, obs, start, goal, alpha0 = _setup(T=T, n_obs=n_obs, B=B, slots=slots, seed=B, **over)
+    args, tr, obs, start, goal, alpha0 = _setup(T=T, n_obs=n_obs, B=B, seed=B, **over)
     a, fs, is_ = _gpu_optimize(tr, mode, alpha0, start, goal)
     ca, cfs, cis = _mirror(args, tr, obs, mode).optimize(alpha0, start, goal)
     is_g, fs_g = is_.cpu().numpy(), fs.cpu().numpy()
@@ -130,7 +126,7 @@ def test_optimize_bit_exact_strict(cuda_ready, mode, slots, T, n_obs, B, over):
     assert len(bad) == 0, (len(bad), bad[:5], is_g[bad[:3]], cis[bad[:3]])
     assert np.array_equal(a.cpu().numpy(), ca)
     assert np.array_equal(fs_g[:, :6], cfs[:, :6])
-    assert tr.handle.launch_geometry(B)["trajectories_per_warp"] == slots
+    assert tr.handle.launch_geometry(B)["trajectories_per_warp"] == gpw
 
 
 def test_budgeted_launches_and_resume_bit_exact(cuda_ready):
@@ -225,19 +221,20 @@ def test_host_buffer_entry_equals_device_path(cuda_ready):
     assert res.done.all()
 
 
-def test_result_independent_of_slots_and_batch_position(cuda_ready):
-    """Batch-vs-loop consistency: a trajectory's result does not depend on how many share its warp,
-    where it sits in the batch, or what its neighbours are (fast-math mode, the product default)."""
-    args, tr1, obs, start, goal, alpha0 = _setup(B=300, strict=False, slots=1, seed=4)
-    a1, fs1, is1 = _gpu_optimize(tr1, "bls", alpha0, start, goal)
-    _, tr4, *_ = _setup(B=300, strict=False, slots=4, seed=4)
+def test_result_independent_of_batch_position(cuda_ready):
+    """Batch-vs-loop consistency: a trajectory's result does not depend on where it sits in the
+    batch, which trajectory shares its warp, or the batch size (fast-math mode, the product default)."""
+    args, tr, obs, start, goal, alpha0 = _setup(B=300, strict=False, seed=4)
+    a1, fs1, is1 = _gpu_optimize(tr, "bls", alpha0, start, goal)
     perm = np.random.default_rng(0).permutation(300)
-    a4, fs4, is4 = _gpu_optimize(tr4, "bls", alpha0[perm], start[perm], goal[perm])
+    a4, fs4, is4 = _gpu_optimize(tr, "bls", alpha0[perm], start[perm], goal[perm])
     assert np.array_equal(a1.cpu().numpy()[perm], a4.cpu().numpy())
     assert np.array_equal(is1.cpu().numpy()[perm], is4.cpu().numpy())
+    a7, _, is7 = _gpu_optimize(tr, "bls", alpha0[:7], start[:7], goal[:7])
+    assert np.array_equal(a1.cpu().numpy()[:7], a7.cpu().numpy()) and np.array_equal(is1.cpu().numpy()[:7], is7.cpu().numpy())
     # identical problems -> identical rows
     rep = np.repeat(alpha0[:1], 64, 0)
-    ar, _, isr = _gpu_optimize(tr4, "bls", rep, np.repeat(start[:1], 64, 0), np.repeat(goal[:1], 64, 0))
+    ar, _, isr = _gpu_optimize(tr, "bls", rep, np.repeat(start[:1], 64, 0), np.repeat(goal[:1], 64, 0))
     assert (ar.cpu().numpy() == ar.cpu().numpy()[0]).all() and (isr.cpu().numpy() == isr.cpu().numpy()[0]).all()
 
 

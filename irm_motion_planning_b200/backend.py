@@ -13,7 +13,7 @@ from typing import Optional
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libfgd_b200.so")
+LIB_PATH = os.environ.get("FGD_LIBRARY", os.path.join(_PKG, "libfgd_b200.so"))   # override: debugging builds only
 
 FGD_ABI_VERSION = 1
 FGD_MAX_T = 256

@@ -14,13 +14,14 @@ using namespace fgd;
 struct FgdHandle {
     FgdConfig cfg;
     DevParams base;            // everything except the per-call batch pointers
-    int T, TP, LPT, R;
+    int T, TP, LPT, R, variant = 0;
     bool k_in_smem;
     int device, num_sms, max_smem_optin;
     float *d_Kt = nullptr, *d_dKt = nullptr;
     float *d_obs[2] = {nullptr, nullptr};
     int obs_active = 0, obs_count = 0;
     unsigned *d_queue = nullptr;
+    int *h_dbg = nullptr, *d_dbg = nullptr;   // FGD_DEBUG_MARK builds: host-mapped progress markers
     cudaEvent_t obs_event = nullptr, launch_event = nullptr;
     bool obs_event_pending = false, launch_event_pending = false;
     int last_cuda_error = 0;
@@ -43,10 +44,13 @@ struct Geometry { int gpw, grid, block, smem; };
 
 // lane mapping by trajectory length: LPT lanes per trajectory, R adjacent rows per lane (TP = LPT*R >= T)
 struct Mapping { int LPT, R; };
-inline Mapping mapping_for(int T) { return T <= 32 ? Mapping{8, 4} : (T <= 64 ? Mapping{16, 4} : (T <= 128 ? Mapping{32, 4} : Mapping{32, 8})); }
+inline Mapping mapping_for(int T) { return T <= 64 ? Mapping{32, 2} : (T <= 128 ? Mapping{32, 4} : Mapping{32, 8}); }
 
-// (LPT, R, KS, NW, MINB): the instantiated kernels.  NW warps per CTA, MINB = min CTAs per SM (register cap).
-#define FGD_FOR_CONFIGS(X) X(8, 4, true, 4, 4) X(16, 4, true, 4, 4) X(32, 4, true, 4, 4) X(32, 8, false, 4, 2)
+// (variant, LPT, R, KS, NW, MINB): the instantiated kernels.  NW warps per CTA, MINB = min CTAs per SM
+// (register cap).  Variant 0 is the default; the others exist for tuning (env FGD_VARIANT).
+#define FGD_FOR_CONFIGS(X) \
+    X(0, 32, 2, true, 4, 4) X(0, 32, 4, true, 4, 3) X(0, 32, 8, false, 4, 2) \
+    X(1, 32, 2, true, 8, 2) X(2, 32, 2, true, 2, 8)
 
 template <int LPT, int R, bool STRICT, bool KS, int NW, int MINB>
 cudaError_t launch_opt(const DevParams &p, int grid, size_t smem, cudaStream_t st)
@@ -78,18 +82,28 @@ cudaError_t launch_eval(const DevParams &p, const EvalPtrs &e, int grid, size_t 
     return cudaGetLastError();
 }
 
-int warps_per_cta(int LPT, int R)
+int g_variant = 0;
+
+bool variant_exists(int v, int LPT, int R)
 {
-#define X(L_, R_, KS_, NW_, MB_) if (LPT == L_ && R == R_) return NW_;
+#define X(V_, L_, R_, KS_, NW_, MB_) if (v == V_ && LPT == L_ && R == R_) return true;
+    FGD_FOR_CONFIGS(X)
+#undef X
+    return false;
+}
+
+int warps_per_cta(int v, int LPT, int R)
+{
+#define X(V_, L_, R_, KS_, NW_, MB_) if (v == V_ && LPT == L_ && R == R_) return NW_;
     FGD_FOR_CONFIGS(X)
 #undef X
     return 4;
 }
 
-cudaError_t dispatch_opt(int LPT, int R, bool strict, const DevParams &p, int grid, size_t smem, cudaStream_t st)
+cudaError_t dispatch_opt(int v, int LPT, int R, bool strict, const DevParams &p, int grid, size_t smem, cudaStream_t st)
 {
-#define X(L_, R_, KS_, NW_, MB_)                                                             \
-    if (LPT == L_ && R == R_)                                                                 \
+#define X(V_, L_, R_, KS_, NW_, MB_)                                                         \
+    if (v == V_ && LPT == L_ && R == R_)                                                      \
         return strict ? launch_opt<L_, R_, true, KS_, NW_, MB_>(p, grid, smem, st)            \
                       : launch_opt<L_, R_, false, KS_, NW_, MB_>(p, grid, smem, st);
     FGD_FOR_CONFIGS(X)
@@ -97,10 +111,10 @@ cudaError_t dispatch_opt(int LPT, int R, bool strict, const DevParams &p, int gr
     return cudaErrorInvalidValue;
 }
 
-int dispatch_occ(int LPT, int R, bool strict, size_t smem)
+int dispatch_occ(int v, int LPT, int R, bool strict, size_t smem)
 {
-#define X(L_, R_, KS_, NW_, MB_)                                                             \
-    if (LPT == L_ && R == R_)                                                                 \
+#define X(V_, L_, R_, KS_, NW_, MB_)                                                         \
+    if (v == V_ && LPT == L_ && R == R_)                                                      \
         return strict ? occupancy_opt<L_, R_, true, KS_, NW_, MB_>(smem) : occupancy_opt<L_, R_, false, KS_, NW_, MB_>(smem);
     FGD_FOR_CONFIGS(X)
 #undef X
@@ -109,8 +123,8 @@ int dispatch_occ(int LPT, int R, bool strict, size_t smem)
 
 cudaError_t dispatch_eval(int LPT, int R, bool strict, const DevParams &p, const EvalPtrs &e, int grid, size_t smem, cudaStream_t st)
 {
-#define X(L_, R_, KS_, NW_, MB_)                                                             \
-    if (LPT == L_ && R == R_)                                                                 \
+#define X(V_, L_, R_, KS_, NW_, MB_)                                                         \
+    if (V_ == 0 && LPT == L_ && R == R_)                                                      \
         return strict ? launch_eval<L_, R_, true, KS_, NW_>(p, e, grid, smem, st)             \
                       : launch_eval<L_, R_, false, KS_, NW_>(p, e, grid, smem, st);
     FGD_FOR_CONFIGS(X)
@@ -121,11 +135,11 @@ cudaError_t dispatch_eval(int LPT, int R, bool strict, const DevParams &p, const
 Geometry geometry(const FgdHandle *h, int B, int n_obs)
 {
     Geometry g;
-    const int nw = warps_per_cta(h->LPT, h->R);
+    const int nw = warps_per_cta(h->variant, h->LPT, h->R);
     g.gpw = 32 / h->LPT;
     g.block = nw * 32;
     g.smem = (int)make_layout(h->T, h->TP, n_obs, h->k_in_smem, nw * g.gpw).bytes();
-    const int occ = dispatch_occ(h->LPT, h->R, h->cfg.strict_math != 0, (size_t)g.smem);
+    const int occ = dispatch_occ(h->variant, h->LPT, h->R, h->cfg.strict_math != 0, (size_t)g.smem);
     const long long per_cta = (long long)nw * g.gpw;
     const long long need = ((long long)B + per_cta - 1) / per_cta;
     const long long cap = (long long)occ * h->num_sms;
@@ -143,6 +157,7 @@ void fill_params(const FgdHandle *h, DevParams &p, int mode, int B, float *alpha
     p.obs = h->d_obs[h->obs_active];
     p.alpha = alpha; p.start = start; p.goal = goal; p.fstate = fstate; p.istate = istate;
     p.queue = h->d_queue;
+    p.dbg = h->d_dbg;
 }
 
 int wait_obstacles(FgdHandle *h, cudaStream_t st)
@@ -165,7 +180,7 @@ int run_optimize(FgdHandle *h, int mode, int B, float *d_alpha, const float *d_s
     fill_params(h, p, mode, B, d_alpha, d_start, d_goal, d_fstate, d_istate, budget);
     const Geometry g = geometry(h, B, p.n_obs);
     CK(cudaMemsetAsync(h->d_queue, 0, sizeof(unsigned), st));
-    CK(dispatch_opt(h->LPT, h->R, h->cfg.strict_math != 0, p, g.grid, (size_t)g.smem, st));
+    CK(dispatch_opt(h->variant, h->LPT, h->R, h->cfg.strict_math != 0, p, g.grid, (size_t)g.smem, st));
     h->launches += 1;
     CK(cudaEventRecord(h->launch_event, st));
     h->launch_event_pending = true;
@@ -228,6 +243,7 @@ int fgd_create(const FgdConfig *cfg, FgdHandle **out)
     CKC(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device));
     CKC(cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
     // K and dK go to shared memory when both fit beside the operand buffers of at least one slot per warp
+    if (const char *e = std::getenv("FGD_VARIANT")) { const int v = std::atoi(e); if (variant_exists(v, h->LPT, h->R)) h->variant = v; }
     h->k_in_smem = h->R <= 4;     // T <= 128: 2*T*TP*4 B <= 128 KB; T = 256 streams K rows from L2
 
     std::vector<float> kt((size_t)T * h->TP, 0.0f), dkt((size_t)T * h->TP, 0.0f);
@@ -242,6 +258,11 @@ int fgd_create(const FgdConfig *cfg, FgdHandle **out)
         CKC(cudaMemset(h->d_obs[i], 0, (size_t)cfg->obstacle_capacity * 2 * 4));
     }
     CKC(cudaMalloc(&h->d_queue, sizeof(unsigned)));
+#ifdef FGD_DEBUG_MARK
+    CKC(cudaHostAlloc(&h->h_dbg, 4096 * sizeof(int), cudaHostAllocMapped));
+    std::memset(h->h_dbg, 0, 4096 * sizeof(int));
+    CKC(cudaHostGetDevicePointer(&h->d_dbg, h->h_dbg, 0));
+#endif
     CKC(cudaEventCreateWithFlags(&h->obs_event, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&h->launch_event, cudaEventDisableTiming));
 #undef CKC
@@ -323,7 +344,7 @@ int fgd_eval_cost_grad(FgdHandle *h, int32_t B, const float *d_alpha, const floa
         p.lam_max = lambda_max_cost; p.oml = 1.0f - p.lam_max; p.w_avg = p.oml * p.inv_T;
     }
     EvalPtrs e{lambda_sg, lambda_jl, d_loss, d_toc, d_grad, d_q, d_v, d_fulfilled};
-    const int nw = warps_per_cta(h->LPT, h->R), per_cta = nw * (32 / h->LPT);
+    const int nw = warps_per_cta(0, h->LPT, h->R), per_cta = nw * (32 / h->LPT);
     const size_t smem = make_layout(h->T, h->TP, p.n_obs, h->k_in_smem, per_cta).bytes();
     long long need = ((long long)B + per_cta - 1) / per_cta, cap = (long long)h->num_sms * 4;
     const int grid = (int)(need < cap ? need : cap);
@@ -400,6 +421,10 @@ int fgd_launch_geometry(const FgdHandle *h, int32_t B, int32_t *grid, int32_t *b
 }
 
 int64_t fgd_kernel_launches(const FgdHandle *h) { return h ? h->launches : 0; }
+
+#ifdef FGD_DEBUG_MARK
+int *fgd_debug_buffer(FgdHandle *h) { return h->h_dbg; }
+#endif
 
 int fgd_measure_fp32_peak(FgdHandle *h, double *tflops_out, void *stream)
 {

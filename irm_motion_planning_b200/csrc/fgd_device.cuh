@@ -1,9 +1,12 @@
 // fgd_device.cuh -- device-side building blocks of the batched FGD iteration (sm_100a).
 //
-// Mapping.  A trajectory is owned by a GROUP of LPT lanes
-// (LPT = 8, 16 or 32; a warp carries 32/LPT independent trajectories side by
-// side).  Lane l of the group owns the R adjacent time samples t = R*l .. R*l+R-1
-// (R = 4 or 8).  The RKHS contraction produces rows t of q = K alpha J and
+// Mapping.  A trajectory is owned by a GROUP of LPT lanes.
+// The shipped configurations use LPT = 32: one warp per trajectory.  (The code is
+// written for LPT = 8/16 as well -- 32/LPT trajectories side by side in a warp --
+// but on B200 those variants deadlocked at full-mask collectives after intra-warp
+// divergence and are not instantiated; see DESIGN.md "open issues".)
+// Lane l of the group owns the R adjacent time samples t = R*l .. R*l+R-1
+// (R = 2, 4 or 8).  The RKHS contraction produces rows t of q = K alpha J and
 // v = dK alpha J in the lane that then does forward kinematics, the obstacle
 // potential and the penalty terms for those samples -- no shared-memory round
 // trip between the two.  K and dK are staged once per CTA in shared memory,
@@ -12,6 +15,10 @@
 // (alpha' or the q/v-gradients) sit in per-group shared buffers and are broadcast
 // inside the group.  Reductions over t: lane-serial over the R rows, then an
 // xor butterfly over the LPT lanes -- the order the mirror oracle reproduces.
+//
+// The groups of a warp execute the contraction, the cost phase, the gradient
+// phase and the normalisation as ONE converged instruction stream; group-specific
+// decisions only predicate what is committed.
 //
 // Compiled with -fmad=false: every fused multiply-add is an explicit fmaf(), so
 // the operation sequence is the documented one (bit-exact against the oracle in
@@ -43,6 +50,7 @@ struct DevParams {
     float *fstate;
     int *istate;
     unsigned *queue;
+    int *dbg;                // optional host-mapped progress markers (debug builds only)
 };
 
 struct EvalPtrs {
@@ -73,35 +81,41 @@ struct Group {
     }
 };
 
+// Group collectives.  They are always executed by all 32 lanes of the warp (the kernels keep
+// the groups of a warp converged around them), so the full mask with width = LPT is legal and
+// compiles to one SHFL per step.
 template <int LPT>
-__device__ __forceinline__ float gsum(float v, unsigned mask)
+__device__ __forceinline__ float gsum(float v)
 {
 #pragma unroll
-    for (int o = LPT / 2; o >= 1; o >>= 1) v = v + __shfl_xor_sync(mask, v, o);
+    for (int o = LPT / 2; o >= 1; o >>= 1) v = v + __shfl_xor_sync(FULL, v, o, LPT);
     return v;
 }
 
 template <int LPT>
-__device__ __forceinline__ float gmax(float v, unsigned mask)
+__device__ __forceinline__ float gmax(float v)
 {
 #pragma unroll
-    for (int o = LPT / 2; o >= 1; o >>= 1) v = fmaxf(v, __shfl_xor_sync(mask, v, o));
+    for (int o = LPT / 2; o >= 1; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, o, LPT));
     return v;
 }
 
 template <int LPT>
-__device__ __forceinline__ int gmin_int(int v, unsigned mask)
+__device__ __forceinline__ int gmin_int(int v)
 {
 #pragma unroll
-    for (int o = LPT / 2; o >= 1; o >>= 1) v = min(v, __shfl_xor_sync(mask, v, o));
+    for (int o = LPT / 2; o >= 1; o >>= 1) v = min(v, __shfl_xor_sync(FULL, v, o, LPT));
     return v;
 }
 
 template <int LPT>
-__device__ __forceinline__ bool gall(bool pred, unsigned mask)
+__device__ __forceinline__ float gbcast(float v, int src_lane_in_group) { return __shfl_sync(FULL, v, src_lane_in_group, LPT); }
+
+template <int LPT>
+__device__ __forceinline__ bool gall(bool pred, const Group<LPT> &G)
 {
-    if constexpr (LPT == 32) return __all_sync(FULL, pred);
-    return (__ballot_sync(mask, pred) & mask) == mask;
+    const unsigned b = __ballot_sync(FULL, pred);
+    return (b & G.mask) == G.mask;
 }
 
 __device__ __forceinline__ float ss3(float a, float b, float c) { return fmaf(c, c, fmaf(b, b, a * a)); }
@@ -161,18 +175,30 @@ __device__ __forceinline__ void contract(const float *__restrict__ kp, const flo
 #pragma unroll 5
     for (int k = 0; k < T; ++k) {
         float kv[R], dv[R];
-#pragma unroll
-        for (int r4 = 0; r4 < R; r4 += 4) {
-            float4 a, b;
+        if constexpr (R == 2) {
+            float2 a, b;
             if constexpr (KS) {
-                a = *reinterpret_cast<const float4 *>(kp + r4);
-                b = *reinterpret_cast<const float4 *>(dp + r4);
+                a = *reinterpret_cast<const float2 *>(kp);
+                b = *reinterpret_cast<const float2 *>(dp);
             } else {
-                a = __ldg(reinterpret_cast<const float4 *>(kp + r4));
-                b = __ldg(reinterpret_cast<const float4 *>(dp + r4));
+                a = __ldg(reinterpret_cast<const float2 *>(kp));
+                b = __ldg(reinterpret_cast<const float2 *>(dp));
             }
-            kv[r4] = a.x; kv[r4 + 1] = a.y; kv[r4 + 2] = a.z; kv[r4 + 3] = a.w;
-            dv[r4] = b.x; dv[r4 + 1] = b.y; dv[r4 + 2] = b.z; dv[r4 + 3] = b.w;
+            kv[0] = a.x; kv[1] = a.y; dv[0] = b.x; dv[1] = b.y;
+        } else {
+#pragma unroll
+            for (int r4 = 0; r4 < R; r4 += 4) {
+                float4 a, b;
+                if constexpr (KS) {
+                    a = *reinterpret_cast<const float4 *>(kp + r4);
+                    b = *reinterpret_cast<const float4 *>(dp + r4);
+                } else {
+                    a = __ldg(reinterpret_cast<const float4 *>(kp + r4));
+                    b = __ldg(reinterpret_cast<const float4 *>(dp + r4));
+                }
+                kv[r4] = a.x; kv[r4 + 1] = a.y; kv[r4 + 2] = a.z; kv[r4 + 3] = a.w;
+                dv[r4] = b.x; dv[r4 + 1] = b.y; dv[r4 + 2] = b.z; dv[r4 + 3] = b.w;
+            }
         }
         kp += TP; dp += TP;
         const float4 xa = x1[k];
@@ -265,7 +291,7 @@ __device__ __forceinline__ void cost_phase(const DevParams &p, const float2 *__r
             const float w = vb * p.inv_vmax;
             const bool mv = p.cvdl ? (fabsf(vb) > p.v_hi) : true;
             f3[b] = mv ? 0.5f * (w * w) : 0.0f;
-            if (valid && (!(qb <= p.qmax) || !(qb >= p.qmin) || !(fabsf(vb) <= p.vmax))) lim_ok = false;
+            lim_ok = lim_ok & (!valid | ((qb <= p.qmax) & (qb >= p.qmin) & (fabsf(vb) <= p.vmax)));
         }
         if (valid) {
             part_c = part_c + c;
@@ -275,13 +301,13 @@ __device__ __forceinline__ void cost_phase(const DevParams &p, const float2 *__r
         }
     }
     // max / first argmax / mean over t
-    const float maxc = gmax<LPT>(lmax, G.mask);
+    const float maxc = gmax<LPT>(lmax);
     int cand = 0x7fffffff;
 #pragma unroll
     for (int r = R - 1; r >= 0; --r)
         if ((t0 + r) < T && cost[r] == maxc) cand = t0 + r;
-    Rw.amax = gmin_int<LPT>(cand, G.mask);
-    const float avg = gsum<LPT>(part_c, G.mask) / p.fT;
+    Rw.amax = gmin_int<LPT>(cand);
+    const float avg = gsum<LPT>(part_c) / p.fT;
     toc = fmaf(p.lam_max, maxc, p.oml * avg);
 
     // start / goal rows
@@ -295,16 +321,16 @@ __device__ __forceinline__ void cost_phase(const DevParams &p, const float2 *__r
         }
 #pragma unroll
     for (int b = 0; b < 3; ++b) { Rw.d0[b] = Rw.q[0][b] - start[b]; Rw.dT[b] = qT[b] - goal[b]; }
-    const float ssp0 = __shfl_sync(G.mask, ss3(Rw.d0[0], Rw.d0[1], Rw.d0[2]), G.base);
-    const float ssv0 = __shfl_sync(G.mask, ss3(Rw.v[0][0], Rw.v[0][1], Rw.v[0][2]), G.base);
-    const float sspT = __shfl_sync(G.mask, ss3(Rw.dT[0], Rw.dT[1], Rw.dT[2]), G.base + lT);
-    const float ssvT = __shfl_sync(G.mask, ss3(vT[0], vT[1], vT[2]), G.base + lT);
+    const float ssp0 = gbcast<LPT>(ss3(Rw.d0[0], Rw.d0[1], Rw.d0[2]), 0);
+    const float ssv0 = gbcast<LPT>(ss3(Rw.v[0][0], Rw.v[0][1], Rw.v[0][2]), 0);
+    const float sspT = gbcast<LPT>(ss3(Rw.dT[0], Rw.dT[1], Rw.dT[2]), lT);
+    const float ssvT = gbcast<LPT>(ss3(vT[0], vT[1], vT[2]), lT);
     const float sg = (0.5f * ssp0 + 0.5f * sspT) + (0.5f * ssv0 + 0.5f * ssvT);
-    const float jl = gsum<LPT>(part_p, G.mask) / p.fT + gsum<LPT>(part_v, G.mask) / p.fT;
+    const float jl = gsum<LPT>(part_p) / p.fT + gsum<LPT>(part_v) / p.fT;
     loss = fmaf(lam_jl, jl, fmaf(lam_sg, sg, toc));
     const bool ends_ok = (sqrtf(ssp0) < p.eps_pos) && (sqrtf(sspT) < p.eps_pos) &&
                          (sqrtf(ssv0) < p.eps_vel) && (sqrtf(ssvT) < p.eps_vel);
-    ful = (ends_ok && gall<LPT>(lim_ok, G.mask)) ? 1 : 0;
+    ful = (ends_ok && gall<LPT>(lim_ok, G)) ? 1 : 0;
 }
 
 // ---------------------------------------------------------------------------
@@ -315,13 +341,12 @@ __device__ __forceinline__ void cost_phase(const DevParams &p, const float2 *__r
 // ---------------------------------------------------------------------------
 template <int LPT, int R>
 __device__ __forceinline__ void grad_phase(const DevParams &p, const Group<LPT> &G, const Rows<R> &Rw, float lam_sg, float lam_jl,
-                                           float4 *XA, float4 *XB)
+                                           float4 *XA, float4 *XB, bool commit)
 {
     const int T = p.T;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const int t = G.gl * R + r;
-        if (t >= T) continue;
         const float wt = (t == Rw.amax) ? (p.lam_max + p.w_avg) : p.w_avg;
         const float cgx = wt * Rw.gx[r], cgy = wt * Rw.gy[r];
         float xs[3], ys[3];
@@ -346,8 +371,10 @@ __device__ __forceinline__ void grad_phase(const DevParams &p, const Group<LPT> 
             gq[k] = fmaf(lam_jl, jpg, fmaf(lam_sg, sgp, tg));
             gv[k] = fmaf(lam_jl, jvg, lam_sg * sgv);
         }
-        XA[t] = make_float4(gq[0], gq[1], gq[2], 0.0f);
-        XB[t] = make_float4(-gv[0], -gv[1], -gv[2], 0.0f);
+        if (commit && t < T) {
+            XA[t] = make_float4(gq[0], gq[1], gq[2], 0.0f);
+            XB[t] = make_float4(-gv[0], -gv[1], -gv[2], 0.0f);
+        }
     }
 }
 

@@ -4,6 +4,18 @@
 #include "fgd_device.cuh"
 #include "../../include/fgd_b200.h"
 
+#ifdef FGD_DEBUG_TRACE
+#include <cstdio>
+#define TRACE(...) do { if (blockIdx.x == 0 && threadIdx.x < 32 && (threadIdx.x & 15) == 0) printf(__VA_ARGS__); } while (0)
+#else
+#define TRACE(...) do { } while (0)
+#endif
+#ifdef FGD_DEBUG_MARK
+#define MARK(id) do { if (p.dbg && blockIdx.x == 0) { volatile int *d_ = p.dbg; d_[threadIdx.x] = (id); } } while (0)
+#else
+#define MARK(id) do { } while (0)
+#endif
+
 namespace fgd {
 
 // shared-memory carve-up, identical on host and device
@@ -90,97 +102,77 @@ __device__ __forceinline__ void begin_outer_eval(const DevParams &p, const Group
     kind = K_EVAL0;
 }
 
-// Pull the next unfinished trajectory from the batch queue into this group.
-// Called with the lanes of ONE group converged (possibly diverged from the rest of the warp).
+// Pull the next unfinished trajectory from the batch queue into every group that asks for one.
+// Executed by the whole (converged) warp; `need` is group-uniform.
 template <int LPT, int R>
-__device__ __forceinline__ void fetch_slot(const DevParams &p, const Group<LPT> &G, Slot &st, int &kind, float (&a)[R][3], float4 *XA)
+__device__ __forceinline__ void fetch_slot(const DevParams &p, const Group<LPT> &G, bool need, Slot &st, int &kind, float (&a)[R][3])
 {
     for (;;) {
+        __syncwarp();
+        if (!__any_sync(FULL, need)) break;
         unsigned idx = 0;
-        if (G.gl == 0) idx = atomicAdd(p.queue, 1u);
-        idx = __shfl_sync(G.mask, idx, G.base);
-        if (idx >= (unsigned)p.B) { st.traj = -1; kind = K_IDLE; return; }
-        const int *is = p.istate + (size_t)idx * FGD_ISTATE;
-        const int status = is[FGD_I_STATUS];
-        if (status == FGD_ST_DONE) continue;
-        const float *fs = p.fstate + (size_t)idx * FGD_FSTATE;
-        st.traj = (int)idx;
-        st.done_iters = 0; st.j = 0; st.alpha_norm = 0.0f;
-        if (status == FGD_ST_FRESH) {
-            st.lam_sg = p.lam_sg0; st.lam_jl = p.lam_jl0;
-            st.lr = (p.mode == 0) ? p.bls_lr0 : p.gd_lr[0];
-            st.outer = 0; st.inner = 0; st.inner_total = 0; st.cand_evals = 0; st.accepts = 0; st.ful = 0; st.hash = 0u;
-            st.loss = 0.0f; st.toc = 0.0f; st.last_new = 0.0f;
-        } else {
-            st.lam_sg = fs[FGD_F_LAM_SG]; st.lam_jl = fs[FGD_F_LAM_JL]; st.lr = fs[FGD_F_LR];
-            st.loss = fs[FGD_F_LOSS]; st.toc = fs[FGD_F_TOC]; st.last_new = fs[FGD_F_LAST_NEW_LOSS];
-            st.outer = is[FGD_I_OUTER]; st.inner = is[FGD_I_INNER]; st.inner_total = is[FGD_I_INNER_TOTAL];
-            st.cand_evals = is[FGD_I_CAND_EVALS]; st.accepts = is[FGD_I_ACCEPTS]; st.ful = is[FGD_I_FULFILLED];
-            st.hash = (unsigned)is[FGD_I_HASH];
-        }
+        if (need && G.gl == 0) idx = atomicAdd(p.queue, 1u);
+        __syncwarp();
+        idx = __shfl_sync(FULL, idx, 0, LPT);
+        if (need) {
+            if (idx >= (unsigned)p.B) {
+                st.traj = -1; kind = K_IDLE; need = false;
+            } else {
+                const int *is = p.istate + (size_t)idx * FGD_ISTATE;
+                const int status = is[FGD_I_STATUS];
+                if (status != FGD_ST_DONE) {            // DONE: finished in an earlier launch, take the next one
+                    const float *fs = p.fstate + (size_t)idx * FGD_FSTATE;
+                    st.traj = (int)idx;
+                    st.done_iters = 0; st.j = 0; st.alpha_norm = 0.0f;
+                    if (status == FGD_ST_FRESH) {
+                        st.lam_sg = p.lam_sg0; st.lam_jl = p.lam_jl0;
+                        st.lr = (p.mode == 0) ? p.bls_lr0 : p.gd_lr[0];
+                        st.outer = 0; st.inner = 0; st.inner_total = 0; st.cand_evals = 0; st.accepts = 0; st.ful = 0; st.hash = 0u;
+                        st.loss = 0.0f; st.toc = 0.0f; st.last_new = 0.0f;
+                    } else {
+                        st.lam_sg = fs[FGD_F_LAM_SG]; st.lam_jl = fs[FGD_F_LAM_JL]; st.lr = fs[FGD_F_LR];
+                        st.loss = fs[FGD_F_LOSS]; st.toc = fs[FGD_F_TOC]; st.last_new = fs[FGD_F_LAST_NEW_LOSS];
+                        st.outer = is[FGD_I_OUTER]; st.inner = is[FGD_I_INNER]; st.inner_total = is[FGD_I_INNER_TOTAL];
+                        st.cand_evals = is[FGD_I_CAND_EVALS]; st.accepts = is[FGD_I_ACCEPTS]; st.ful = is[FGD_I_FULFILLED];
+                        st.hash = (unsigned)is[FGD_I_HASH];
+                    }
 #pragma unroll
-        for (int b = 0; b < 3; ++b) { st.start[b] = p.start[(size_t)idx * 3 + b]; st.goal[b] = p.goal[(size_t)idx * 3 + b]; }
-        const float *ap = p.alpha + (size_t)idx * p.T * 3;
+                    for (int b = 0; b < 3; ++b) { st.start[b] = p.start[(size_t)idx * 3 + b]; st.goal[b] = p.goal[(size_t)idx * 3 + b]; }
+                    const float *ap = p.alpha + (size_t)idx * p.T * 3;
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int t = G.gl * R + r;
-            const bool ok = t < p.T;
-            a[r][0] = ok ? ap[t * 3] : 0.0f; a[r][1] = ok ? ap[t * 3 + 1] : 0.0f; a[r][2] = ok ? ap[t * 3 + 2] : 0.0f;
+                    for (int r = 0; r < R; ++r) {
+                        const int t = G.gl * R + r;
+                        const bool ok = t < p.T;
+                        a[r][0] = ok ? ap[t * 3] : 0.0f; a[r][1] = ok ? ap[t * 3 + 1] : 0.0f; a[r][2] = ok ? ap[t * 3 + 2] : 0.0f;
+                    }
+                    kind = K_EVAL0;
+                    need = false;
+                }
+            }
         }
-        begin_outer_eval<LPT, R>(p, G, st, kind, a, XA);
-        return;
     }
-}
-
-// End of an inner loop: constraint verdict, lambda escalation, next outer
-// iteration or retirement.   optimizer_BLS.py:196-205, optimizer_GD.py:214-224
-template <int LPT, int R>
-__device__ __forceinline__ void end_inner(const DevParams &p, const Group<LPT> &G, Slot &st, int &kind, float (&a)[R][3], float4 *XA)
-{
-    const bool dual = (p.mode == 0) || (p.max_outer > 1);
-    bool retire = !dual || st.ful;
-    if (!retire) {
-        st.lam_sg = st.lam_sg * p.lam_inc; st.lam_jl = st.lam_jl * p.lam_inc;
-        st.outer += 1; hash_step(st, 4u);
-        retire = st.outer >= p.max_outer;
-    }
-    if (retire) {
-        save_slot<LPT, R>(p, G, st, FGD_ST_DONE, a);
-        fetch_slot<LPT, R>(p, G, st, kind, a, XA);
-        return;
-    }
-    st.inner = 0;
-    if (p.mode == 0) st.lr = p.bls_lr0;       // optimizer_BLS.py:193
-    begin_outer_eval<LPT, R>(p, G, st, kind, a, XA);
-}
-
-// Head of the inner loop (optimizer_BLS.py:155-157): continue with a gradient,
-// stop at the launch budget, or fall through to the constraint check.
-template <int LPT, int R>
-__device__ __forceinline__ void inner_head(const DevParams &p, const Group<LPT> &G, Slot &st, int &kind, float (&a)[R][3], float4 *XA)
-{
-    if (st.inner < p.max_inner) {
-        if (p.budget >= 0 && st.done_iters == p.budget) {
-            save_slot<LPT, R>(p, G, st, FGD_ST_ACTIVE, a);
-            fetch_slot<LPT, R>(p, G, st, kind, a, XA);
-            return;
-        }
-        st.done_iters += 1; st.inner_total += 1;
-        kind = K_BACK;
-        return;
-    }
-    end_inner<LPT, R>(p, G, st, kind, a, XA);
+    __syncwarp();
 }
 
 template <bool KS>
 __device__ __forceinline__ void stage_constants(const DevParams &p, const SmemLayout &L, float *sK, float *sdK, float2 *sObs, int nthreads)
 {
+    // trip counts are CTA-uniform (the bound check is inside), so no warp diverges ahead of the barrier
     if constexpr (KS) {
         const float4 *gK = reinterpret_cast<const float4 *>(p.Kt), *gD = reinterpret_cast<const float4 *>(p.dKt);
         float4 *dK4 = reinterpret_cast<float4 *>(sK), *dD4 = reinterpret_cast<float4 *>(sdK);
-        for (int i = threadIdx.x; i < L.k_floats / 4; i += nthreads) { dK4[i] = __ldg(gK + i); dD4[i] = __ldg(gD + i); }
+        const int n4 = L.k_floats / 4;
+#pragma unroll 1
+        for (int i0 = 0; i0 < n4; i0 += nthreads) {
+            const int i = i0 + threadIdx.x;
+            if (i < n4) { dK4[i] = __ldg(gK + i); dD4[i] = __ldg(gD + i); }
+        }
     }
-    for (int i = threadIdx.x; i < p.n_obs; i += nthreads) sObs[i] = make_float2(p.obs[2 * i], p.obs[2 * i + 1]);
+#pragma unroll 1
+    for (int i0 = 0; i0 < p.n_obs; i0 += nthreads) {
+        const int i = i0 + threadIdx.x;
+        if (i < p.n_obs) sObs[i] = make_float2(p.obs[2 * i], p.obs[2 * i + 1]);
+    }
     __syncthreads();
 }
 
@@ -218,107 +210,147 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
     for (int r = 0; r < R; ++r)
 #pragma unroll
         for (int b = 0; b < 3; ++b) { a[r][b] = 0.0f; d[r][b] = 0.0f; }
-    {
-        Slot st;
-        fetch_slot<LPT, R>(p, G, st, kind, a, XA);
-        *slot = st;
-    }
-
+    bool boot = true;          // first trip: nothing to contract yet, just fill the slots through the common tail
     for (;;) {
-        if (!__any_sync(FULL, kind != K_IDLE)) break;
-        const float4 *x1 = XA, *x2 = (kind == K_BACK) ? XB : XA;
         float y1[R][3], y2[R][3];
-        __syncwarp();
-        contract<R, KS>(kp, dp, T, TP, x1, x2, y1, y2);
-        __syncwarp();
-        if (kind != K_IDLE) {
-        // group-uniform scalars: every lane works on its own register copy and all lanes of the
-        // group write back identical values (race-free by construction)
+        if (!boot) {
+            if (!__any_sync(FULL, kind != K_IDLE)) break;
+            const float4 *x1 = XA, *x2 = (kind == K_BACK) ? XB : XA;
+            __syncwarp();
+            contract<R, KS>(kp, dp, T, TP, x1, x2, y1, y2);
+            __syncwarp();
+        }
+        // Group-uniform scalars live in a register copy of the slot; all lanes of a group compute and
+        // write back identical values.  Both groups of the warp run the same instruction stream; the
+        // per-group state only decides what gets committed.
         Slot st = *slot;
-        __syncwarp(G.mask);
-        if (kind == K_BACK) {
-            // ---- alpha-gradient, normalisation, first candidate ----------------
+        TRACE("lane %d trip boot=%d kind=%d\n", threadIdx.x, (int)boot, kind);
+        const bool is_back = !boot && kind == K_BACK;
+        const bool is_fwd = !boot && (kind == K_EVAL0 || kind == K_CAND);
+        bool want_cand = false;     // write the next candidate into XA
+        bool want_head = false;     // go to the head of the inner loop
+        bool want_end = false;      // inner loop finished: constraint check / lambda escalation
+        bool want_eval = false;     // (re-)evaluate loss and gradient operands at alpha
+
+        __syncwarp();
+        if (__any_sync(FULL, is_back)) {
+            // ---- alpha-gradient, normalisation, first candidate ------------------------------
             float g[R][3];
             backward_rows<R>(p, y1, y2, g);
+            float alpha_norm = 0.0f, scale = 1.0f;
             if (p.mode == 0) {
                 float part = 0.0f;
 #pragma unroll
                 for (int r = 0; r < R; ++r)
                     if (G.gl * R + r < T) part = part + ss3(g[r][0], g[r][1], g[r][2]);
-                const float nrm = sqrtf(gsum<LPT>(part, G.mask));                  // optimizer_BLS.py:165
+                scale = 1.0f / sqrtf(gsum<LPT>(part));                                 // optimizer_BLS.py:165
                 float pb = 0.0f;
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
-#pragma unroll
-                    for (int b = 0; b < 3; ++b) d[r][b] = g[r][b] / nrm;
-                    if (G.gl * R + r < T)
-                        pb = pb + ((g[r][0] + g[r][1]) + g[r][2]) * ((d[r][0] + d[r][1]) + d[r][2]);
+                    const float n0 = g[r][0] * scale, n1 = g[r][1] * scale, n2 = g[r][2] * scale;
+                    if (G.gl * R + r < T) pb = pb + ((g[r][0] + g[r][1]) + g[r][2]) * ((n0 + n1) + n2);
+                    g[r][0] = n0; g[r][1] = n1; g[r][2] = n2;
                 }
-                st.alpha_norm = gsum<LPT>(pb, G.mask);                             // optimizer_BLS.py:166
-                st.j = 0;
-            } else {
+                alpha_norm = gsum<LPT>(pb);                                            // optimizer_BLS.py:166
+            }
+            if (is_back) {
 #pragma unroll
                 for (int r = 0; r < R; ++r)
 #pragma unroll
                     for (int b = 0; b < 3; ++b) d[r][b] = g[r][b];
+                st.alpha_norm = alpha_norm; st.j = 0;
+                want_cand = true;
+                kind = K_CAND;
             }
-            write_candidate<LPT, R>(p, G, st.lr, a, d, XA);
-            kind = K_CAND;
-        } else {
-            // ---- loss (and, if accepted, gradient operands) at alpha or at a candidate
+        }
+        __syncwarp();
+        if (__any_sync(FULL, is_fwd)) {
+            // ---- loss (and, if accepted, gradient operands) at alpha or at a candidate -------
             Rows<R> Rw;
             float loss_c, toc_c;
             int ful_c;
             cost_phase<LPT, R, STRICT>(p, sObs, G, y1, y2, st.start, st.goal, st.lam_sg, st.lam_jl, Rw, loss_c, toc_c, ful_c);
-            if (kind == K_EVAL0) {
-                st.loss = loss_c; st.toc = toc_c; st.ful = ful_c;
-                grad_phase<LPT, R>(p, G, Rw, st.lam_sg, st.lam_jl, XA, XB);
-                inner_head<LPT, R>(p, G, st, kind, a, XA);
-            } else if (p.mode == 0) {
-                // Armijo test   optimizer_BLS.py:141-149
-                st.cand_evals += 1;
-                const float lr = st.lr, loss = st.loss;
-                const float req = loss - (p.bls_alpha * lr) * st.alpha_norm;
-                if (loss_c > req) {
-                    st.lr = lr * p.bls_bm; hash_step(st, 1u);
-                    st.j += 1;
-                    if (st.j < p.max_bls) {
-                        write_candidate<LPT, R>(p, G, st.lr, a, d, XA);
+            bool accept = false;
+            if (is_fwd) {
+                if (kind == K_EVAL0) {
+                    st.loss = loss_c; st.toc = toc_c; st.ful = ful_c;
+                    accept = true; want_head = true;
+                } else {
+                    st.cand_evals += 1;
+                    const float lr = st.lr, loss = st.loss;
+                    const bool minimized = (loss - loss_c < p.eps_loop);               // optimizer_BLS.py:178, optimizer_GD.py:194
+                    bool rejected = false;
+                    if (p.mode == 0) {                                                 // Armijo test, optimizer_BLS.py:141-149
+                        const float req = loss - (p.bls_alpha * lr) * st.alpha_norm;
+                        rejected = loss_c > req;
                     } else {
-                        // every candidate rejected: new_loss := loss (optimizer_BLS.py:170,178)
-                        st.last_new = loss;
-                        const bool minimized = (loss - loss < p.eps_loop);
-                        if (minimized) { hash_step(st, 3u); end_inner<LPT, R>(p, G, st, kind, a, XA); }
-                        else { st.inner += 1; begin_outer_eval<LPT, R>(p, G, st, kind, a, XA); }
+                        st.last_new = loss_c;
                     }
-                } else {
-                    accept_candidate<R>(p, lr, a, d);
-                    grad_phase<LPT, R>(p, G, Rw, st.lam_sg, st.lam_jl, XA, XB);
-                    st.lr = lr * p.bls_bp; st.accepts += 1; hash_step(st, 2u);
-                    st.ful = ful_c; st.toc = toc_c; st.last_new = loss_c;
-                    const bool minimized = (loss - loss_c < p.eps_loop);           // optimizer_BLS.py:178
-                    st.loss = loss_c;
-                    if (minimized) { hash_step(st, 3u); end_inner<LPT, R>(p, G, st, kind, a, XA); }
-                    else { st.inner += 1; inner_head<LPT, R>(p, G, st, kind, a, XA); }
-                }
-            } else {
-                // fixed-step GD   optimizer_GD.py:186-194
-                st.cand_evals += 1;
-                st.last_new = loss_c;
-                if (st.loss - loss_c < p.eps_loop) {
-                    hash_step(st, 3u);
-                    end_inner<LPT, R>(p, G, st, kind, a, XA);
-                } else {
-                    accept_candidate<R>(p, st.lr, a, d);
-                    grad_phase<LPT, R>(p, G, Rw, st.lam_sg, st.lam_jl, XA, XB);
-                    st.loss = loss_c; st.ful = ful_c; st.toc = toc_c;
-                    st.accepts += 1; st.inner += 1; hash_step(st, 2u);
-                    inner_head<LPT, R>(p, G, st, kind, a, XA);
+                    if (rejected) {
+                        st.lr = lr * p.bls_bm; hash_step(st, 1u);
+                        st.j += 1;
+                        if (st.j < p.max_bls) {
+                            want_cand = true;
+                        } else {
+                            // every candidate rejected: new_loss := loss (optimizer_BLS.py:170,178)
+                            st.last_new = loss;
+                            if (loss - loss < p.eps_loop) { hash_step(st, 3u); want_end = true; }
+                            else { st.inner += 1; want_eval = true; }
+                        }
+                    } else if (p.mode == 1 && minimized) {
+                        hash_step(st, 3u); want_end = true;    // GD: the candidate is discarded (optimizer_GD.py:191-192)
+                    } else {
+                        accept_candidate<R>(p, lr, a, d);
+                        accept = true;
+                        if (p.mode == 0) st.lr = lr * p.bls_bp;
+                        st.accepts += 1; hash_step(st, 2u);
+                        st.ful = ful_c; st.toc = toc_c; st.last_new = loss_c; st.loss = loss_c;
+                        if (minimized) { hash_step(st, 3u); want_end = true; }       // BLS keeps the accepted alpha
+                        else { st.inner += 1; want_head = true; }
+                    }
                 }
             }
+            __syncwarp();
+            if (__any_sync(FULL, accept)) grad_phase<LPT, R>(p, G, Rw, st.lam_sg, st.lam_jl, XA, XB, accept);
         }
+        // ---- common tail: loop heads, retirement, refill -------------------------------------
+        bool save_active = false;
+        if (want_head) {                                         // optimizer_BLS.py:155-157
+            if (st.inner < p.max_inner) {
+                if (p.budget >= 0 && st.done_iters == p.budget) save_active = true;
+                else { st.done_iters += 1; st.inner_total += 1; kind = K_BACK; }
+            } else {
+                want_end = true;
+            }
+        }
+        bool retire = false;
+        if (want_end) {                                          // optimizer_BLS.py:196-205, optimizer_GD.py:214-224
+            const bool dual = (p.mode == 0) || (p.max_outer > 1);
+            retire = !dual || st.ful;
+            if (!retire) {
+                st.lam_sg = st.lam_sg * p.lam_inc; st.lam_jl = st.lam_jl * p.lam_inc;
+                st.outer += 1; hash_step(st, 4u);
+                retire = st.outer >= p.max_outer;
+            }
+            if (!retire) {
+                st.inner = 0;
+                if (p.mode == 0) st.lr = p.bls_lr0;              // optimizer_BLS.py:193
+                want_eval = true;
+            }
+        }
+        const bool refill = retire || save_active || boot;
+        TRACE("lane %d tail head=%d end=%d refill=%d kind=%d\n", threadIdx.x, (int)want_head, (int)want_end, (int)refill, kind);
+        __syncwarp();
+        if (__any_sync(FULL, refill)) {
+            if (refill && !boot) save_slot<LPT, R>(p, G, st, retire ? FGD_ST_DONE : FGD_ST_ACTIVE, a);
+            fetch_slot<LPT, R>(p, G, refill, st, kind, a);
+            if (refill) want_eval = (kind != K_IDLE);
+        }
+        TRACE("lane %d after fetch kind=%d traj=%d\n", threadIdx.x, kind, st.traj);
+        if (want_eval) begin_outer_eval<LPT, R>(p, G, st, kind, a, XA);
+        if (want_cand) write_candidate<LPT, R>(p, G, st.lr, a, d, XA);
         *slot = st;
-        }
+        boot = false;
     }
 }
 
@@ -337,7 +369,9 @@ __global__ void __launch_bounds__(NW * 32) fgd_eval_kernel(const __grid_constant
     float *sdK = sK + L.k_floats;
     float2 *sObs = reinterpret_cast<float2 *>(sdK + L.k_floats);
     float4 *sX = reinterpret_cast<float4 *>(sObs + L.obs_pairs);
+    MARK(1);
     stage_constants<KS>(p, L, sK, sdK, sObs, NW * 32);
+    MARK(2);
 
     const Group<LPT> G;
     const int warp = threadIdx.x >> 5;
@@ -369,15 +403,18 @@ __global__ void __launch_bounds__(NW * 32) fgd_eval_kernel(const __grid_constant
             for (int k = 0; k < 3; ++k) { start[k] = p.start[(size_t)b * 3 + k]; goal[k] = p.goal[(size_t)b * 3 + k]; }
         }
         float y1[R][3], y2[R][3];
+        MARK(3);
         __syncwarp();
         contract<R, KS>(kp, dp, T, TP, XA, XA, y1, y2);
+        MARK(4);
         __syncwarp();
-        if (live) {
+        {
             Rows<R> Rw;
             float loss, toc;
             int ful;
             cost_phase<LPT, R, STRICT>(p, sObs, G, y1, y2, start, goal, e.lam_sg, e.lam_jl, Rw, loss, toc, ful);
-            if (G.gl == 0) {
+            MARK(5);
+            if (live && G.gl == 0) {
                 if (e.loss) e.loss[b] = loss;
                 if (e.toc) e.toc[b] = toc;
                 if (e.fulfilled) e.fulfilled[b] = ful;
@@ -385,7 +422,7 @@ __global__ void __launch_bounds__(NW * 32) fgd_eval_kernel(const __grid_constant
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const int t = G.gl * R + r;
-                if (t < T) {
+                if (live && t < T) {
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
                         if (e.q) e.q[((size_t)b * T + t) * 3 + k] = Rw.q[r][k];
@@ -393,7 +430,7 @@ __global__ void __launch_bounds__(NW * 32) fgd_eval_kernel(const __grid_constant
                     }
                 }
             }
-            if (e.grad) grad_phase<LPT, R>(p, G, Rw, e.lam_sg, e.lam_jl, XA, XB);
+            if (e.grad) grad_phase<LPT, R>(p, G, Rw, e.lam_sg, e.lam_jl, XA, XB, live);
         }
         if (e.grad) {
             __syncwarp();
@@ -411,8 +448,10 @@ __global__ void __launch_bounds__(NW * 32) fgd_eval_kernel(const __grid_constant
                 }
             }
         }
+        MARK(6);
         __syncwarp();
     }
+    MARK(7);
 }
 
 // ---------------------------------------------------------------------------

@@ -27,6 +27,8 @@
  *                                                  (environment.py:43,57)
  *   - (q-mean)/std, /std^2, v/vmax, /T in the limit penalties multiply by
  *     host-rounded reciprocals                     (trajectory.py:217,232,247,260)
+ *   - the gradient is normalised by multiplying with 1/||g|| instead of dividing
+ *                                                  (optimizer_BLS.py:165)
  *   - alpha_norm = sum_t (sum_a g[t,a]) * (sum_b n[t,b]), algebraically equal
  *     to sum(g.T @ n)                              (optimizer_BLS.py:166)
  *   - sin/cos: Cody-Waite reduction + cephes minimax polynomials written out
@@ -113,10 +115,10 @@ static void mirror_sincos(float x, float *s_out, float *c_out)
  * xor butterfly LPT/2, ..., 2, 1 over the lanes.  Same mapping table as the CUDA side.   */
 static void mapping_for(int T, int *LPT, int *R)
 {
-    if (T <= 32) { *LPT = 8; *R = 4; }
-    else if (T <= 64) { *LPT = 16; *R = 4; }
-    else if (T <= 128) { *LPT = 32; *R = 4; }
-    else { *LPT = 32; *R = 8; }
+    *LPT = 32;                      /* one warp per trajectory */
+    if (T <= 64) *R = 2;
+    else if (T <= 128) *R = 4;
+    else *R = 8;
 }
 
 static float tree_sum(const float *x, int T)
@@ -340,8 +342,8 @@ static void optimize_one(const MirrorCfg *c, const Derived *d, const float *K, c
             float lr = fs[F_LR];
             if (c->mode == 0) {
                 for (int t = 0; t < T; ++t) rowa[t] = ss3(g[t * 3], g[t * 3 + 1], g[t * 3 + 2]);
-                float nrm = sqrtf(tree_sum(rowa, T));
-                for (int i = 0; i < n; ++i) nh[i] = g[i] / nrm;          /* :165 */
+                float scale = 1.0f / sqrtf(tree_sum(rowa, T));
+                for (int i = 0; i < n; ++i) nh[i] = g[i] * scale;        /* :165 (reciprocal, then multiply) */
                 for (int t = 0; t < T; ++t)
                     rowb[t] = ((g[t * 3] + g[t * 3 + 1]) + g[t * 3 + 2]) * ((nh[t * 3] + nh[t * 3 + 1]) + nh[t * 3 + 2]);
                 float alpha_norm = tree_sum(rowb, T);                    /* :166 */

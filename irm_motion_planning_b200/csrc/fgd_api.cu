@@ -17,7 +17,7 @@ struct FgdHandle {
     int T, TP, LPT, R, variant = 0;
     bool k_in_smem;
     int device, num_sms, max_smem_optin;
-    float *d_Kt = nullptr, *d_dKt = nullptr;
+    float *d_KD = nullptr, *d_KO = nullptr;
     float *d_obs[2] = {nullptr, nullptr};
     int obs_active = 0, obs_count = 0;
     unsigned *d_queue = nullptr;
@@ -49,8 +49,8 @@ inline Mapping mapping_for(int T) { return T <= 64 ? Mapping{32, 2} : (T <= 128 
 // (variant, LPT, R, KS, NW, MINB): the instantiated kernels.  NW warps per CTA, MINB = min CTAs per SM
 // (register cap).  Variant 0 is the default; the others exist for tuning (env FGD_VARIANT).
 #define FGD_FOR_CONFIGS(X) \
-    X(0, 32, 2, true, 4, 4) X(0, 32, 4, true, 4, 3) X(0, 32, 8, false, 4, 2) \
-    X(1, 32, 2, true, 8, 2) X(2, 32, 2, true, 2, 8)
+    X(0, 32, 2, true, 8, 2) X(0, 32, 4, true, 4, 3) X(0, 32, 8, false, 4, 2) \
+    X(1, 32, 2, true, 4, 4) X(2, 32, 2, true, 16, 1)
 
 template <int LPT, int R, bool STRICT, bool KS, int NW, int MINB>
 cudaError_t launch_opt(const DevParams &p, int grid, size_t smem, cudaStream_t st)
@@ -246,13 +246,21 @@ int fgd_create(const FgdConfig *cfg, FgdHandle **out)
     if (const char *e = std::getenv("FGD_VARIANT")) { const int v = std::atoi(e); if (variant_exists(v, h->LPT, h->R)) h->variant = v; }
     h->k_in_smem = h->R <= 4;     // T <= 128: 2*T*TP*4 B <= 128 KB; T = 256 streams K rows from L2
 
-    std::vector<float> kt((size_t)T * h->TP, 0.0f), dkt((size_t)T * h->TP, 0.0f);
-    for (int i = 0; i < T; ++i)
-        for (int k = 0; k < T; ++k) { kt[(size_t)k * h->TP + i] = cfg->h_km[i * T + k]; dkt[(size_t)k * h->TP + i] = cfg->h_dkm[i * T + k]; }
-    CKC(cudaMalloc(&h->d_Kt, kt.size() * 4));
-    CKC(cudaMalloc(&h->d_dKt, dkt.size() * 4));
-    CKC(cudaMemcpy(h->d_Kt, kt.data(), kt.size() * 4, cudaMemcpyHostToDevice));
-    CKC(cudaMemcpy(h->d_dKt, dkt.data(), dkt.size() * 4, cudaMemcpyHostToDevice));
+    // operand table KD[k][lane][2R]: the R row entries K[t][k] then the R entries dK[t][k] of lane's rows t = R*lane + r
+    // and KO[k][lane][R]: the K entries alone (dense half of the backward contraction)
+    std::vector<float> kd((size_t)T * 2 * h->TP, 0.0f), ko((size_t)T * h->TP, 0.0f);
+    for (int k = 0; k < T; ++k)
+        for (int i = 0; i < T; ++i) {
+            const int lane = i / h->R, r = i % h->R;
+            const size_t base = ((size_t)k * h->LPT + lane) * 2 * h->R;
+            kd[base + r] = cfg->h_km[i * T + k];
+            kd[base + h->R + r] = cfg->h_dkm[i * T + k];
+            ko[((size_t)k * h->LPT + lane) * h->R + r] = cfg->h_km[i * T + k];
+        }
+    CKC(cudaMalloc(&h->d_KD, kd.size() * 4));
+    CKC(cudaMemcpy(h->d_KD, kd.data(), kd.size() * 4, cudaMemcpyHostToDevice));
+    CKC(cudaMalloc(&h->d_KO, ko.size() * 4));
+    CKC(cudaMemcpy(h->d_KO, ko.data(), ko.size() * 4, cudaMemcpyHostToDevice));
     for (int i = 0; i < 2; ++i) {
         CKC(cudaMalloc(&h->d_obs[i], (size_t)cfg->obstacle_capacity * 2 * 4));
         CKC(cudaMemset(h->d_obs[i], 0, (size_t)cfg->obstacle_capacity * 2 * 4));
@@ -294,7 +302,7 @@ int fgd_create(const FgdConfig *cfg, FgdHandle **out)
     p.q_hi = cfg->joint_safety_limit * p.qmax;
     p.q_lo = cfg->joint_safety_limit * p.qmin;
     p.v_hi = cfg->joint_safety_limit * p.vmax;
-    p.Kt = h->d_Kt; p.dKt = h->d_dKt;
+    p.KD = h->d_KD; p.KO = h->d_KO;
     *out = h;
     return FGD_OK;
 }
@@ -302,7 +310,7 @@ int fgd_create(const FgdConfig *cfg, FgdHandle **out)
 int fgd_destroy(FgdHandle *h)
 {
     if (!h) return FGD_OK;
-    cudaFree(h->d_Kt); cudaFree(h->d_dKt); cudaFree(h->d_obs[0]); cudaFree(h->d_obs[1]); cudaFree(h->d_queue);
+    cudaFree(h->d_KD); cudaFree(h->d_KO); cudaFree(h->d_obs[0]); cudaFree(h->d_obs[1]); cudaFree(h->d_queue);
     cudaFree(h->s_alpha); cudaFree(h->s_start); cudaFree(h->s_goal); cudaFree(h->s_fstate); cudaFree(h->s_istate);
     if (h->obs_event) cudaEventDestroy(h->obs_event);
     if (h->launch_event) cudaEventDestroy(h->launch_event);

@@ -43,7 +43,8 @@ struct DevParams {
     float gd_lr[16];
     // derived on the host, rounded once to FP32 (same expressions as the oracle)
     float oml, inv_T, w_avg, mean_q, inv_std, inv_std2, inv_vmax, inv_vmax2, q_hi, q_lo, v_hi, fT;
-    const float *Kt, *dKt;   // [T][TP]: Kt[k][i] = K[i][k], zero padded for i >= T
+    const float *KD;         // [T][LPT][2R]: K and dK entries of column k interleaved per lane (zero padded rows >= T)
+    const float *KO;         // [T][LPT][R]:  K entries only (dense half of the backward contraction)
     const float *obs;        // [n_obs][2]
     float *alpha;            // [B][T][3]
     const float *start, *goal;
@@ -159,14 +160,19 @@ __device__ __forceinline__ void sincos_cw(float x, float &S, float &C)
 // RKHS contraction for the trajectory of this lane's group:
 //   y1[r][a] = sum_k K [t_r][k] * x1[k][a]      (trajectory.py:65 / :295)
 //   y2[r][a] = sum_k dK[t_r][k] * x2[k][a]
-// k ascending, one fmaf per term.  K rows come from shared memory (KS) or L2.
-// kp / dp point at this lane's first row entry of column 0.
+// k ascending, one fmaf per term.  KD is the interleaved operand table
+//   KD[k][lane][0..R-1] = K[t_r][k],  KD[k][lane][R..2R-1] = dK[t_r][k]
+// (row stride 2*TP floats, TP = LPT*R compile-time), so a lane fetches all its
+// entries of column k with 2R/4 LDS.128 at immediate offsets.  It comes from
+// shared memory (KS) or, for T > 128, from L2 through the read-only path.
+// SAME = true: x1 == x2 (forward evaluation), one operand load per k.
 // ---------------------------------------------------------------------------
-template <int R, bool KS>
-__device__ __forceinline__ void contract(const float *__restrict__ kp, const float *__restrict__ dp, int T, int TP,
+template <int LPT, int R, bool KS, bool SAME>
+__device__ __forceinline__ void contract(const float *__restrict__ kd, int T,
                                          const float4 *__restrict__ x1, const float4 *__restrict__ x2,
                                          float (&y1)[R][3], float (&y2)[R][3])
 {
+    constexpr int STRIDE = 2 * LPT * R;       // floats per column k
 #pragma unroll
     for (int r = 0; r < R; ++r)
 #pragma unroll
@@ -174,43 +180,92 @@ __device__ __forceinline__ void contract(const float *__restrict__ kp, const flo
 
 #pragma unroll 5
     for (int k = 0; k < T; ++k) {
-        float kv[R], dv[R];
-        if constexpr (R == 2) {
-            float2 a, b;
-            if constexpr (KS) {
-                a = *reinterpret_cast<const float2 *>(kp);
-                b = *reinterpret_cast<const float2 *>(dp);
-            } else {
-                a = __ldg(reinterpret_cast<const float2 *>(kp));
-                b = __ldg(reinterpret_cast<const float2 *>(dp));
-            }
-            kv[0] = a.x; kv[1] = a.y; dv[0] = b.x; dv[1] = b.y;
-        } else {
+        float kv[2 * R];
 #pragma unroll
-            for (int r4 = 0; r4 < R; r4 += 4) {
-                float4 a, b;
-                if constexpr (KS) {
-                    a = *reinterpret_cast<const float4 *>(kp + r4);
-                    b = *reinterpret_cast<const float4 *>(dp + r4);
-                } else {
-                    a = __ldg(reinterpret_cast<const float4 *>(kp + r4));
-                    b = __ldg(reinterpret_cast<const float4 *>(dp + r4));
-                }
-                kv[r4] = a.x; kv[r4 + 1] = a.y; kv[r4 + 2] = a.z; kv[r4 + 3] = a.w;
-                dv[r4] = b.x; dv[r4 + 1] = b.y; dv[r4 + 2] = b.z; dv[r4 + 3] = b.w;
-            }
+        for (int c = 0; c < 2 * R; c += 4) {
+            float4 v;
+            if constexpr (KS) v = *reinterpret_cast<const float4 *>(kd + (size_t)k * STRIDE + c);
+            else v = __ldg(reinterpret_cast<const float4 *>(kd + (size_t)k * STRIDE + c));
+            kv[c] = v.x; kv[c + 1] = v.y; kv[c + 2] = v.z; kv[c + 3] = v.w;
         }
-        kp += TP; dp += TP;
         const float4 xa = x1[k];
-        const float4 xb = x2[k];
+        float4 xb = xa;
+        if constexpr (!SAME) xb = x2[k];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             y1[r][0] = fmaf(kv[r], xa.x, y1[r][0]);
             y1[r][1] = fmaf(kv[r], xa.y, y1[r][1]);
             y1[r][2] = fmaf(kv[r], xa.z, y1[r][2]);
-            y2[r][0] = fmaf(dv[r], xb.x, y2[r][0]);
-            y2[r][1] = fmaf(dv[r], xb.y, y2[r][1]);
-            y2[r][2] = fmaf(dv[r], xb.z, y2[r][2]);
+            y2[r][0] = fmaf(kv[R + r], xb.x, y2[r][0]);
+            y2[r][1] = fmaf(kv[R + r], xb.y, y2[r][1]);
+            y2[r][2] = fmaf(kv[R + r], xb.z, y2[r][2]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Backward contraction  y1 = K G_q (dense),  y2 = dK (-G_v) (sparse).
+// G_v = lam_sg*sgv_g + lam_jl*jv_g is zero except in rows 0 and T-1 and where the
+// velocity limit is violated (trajectory.py:207-212, 258-268), so the dK half only
+// visits the rows flagged in nz[] (bit l of nz[r] <=> row R*l + r is non-zero).
+// Skipped terms are exact zeros, so the result equals the dense sum bit for bit;
+// the visited terms are still accumulated in ascending k.
+// ---------------------------------------------------------------------------
+template <int LPT, int R, bool KS>
+__device__ __forceinline__ void contract_back(const float *__restrict__ ko, const float *__restrict__ kd, int T,
+                                              const float4 *__restrict__ xa_rows, const float4 *__restrict__ xb_rows,
+                                              const unsigned (&nz)[R], float (&y1)[R][3], float (&y2)[R][3])
+{
+    constexpr int SO = LPT * R, SD = 2 * LPT * R;
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { y1[r][a] = 0.0f; y2[r][a] = 0.0f; }
+#pragma unroll 5
+    for (int k = 0; k < T; ++k) {
+        float kv[R];
+        if constexpr (R == 2) {
+            float2 v;
+            if constexpr (KS) v = *reinterpret_cast<const float2 *>(ko + (size_t)k * SO);
+            else v = __ldg(reinterpret_cast<const float2 *>(ko + (size_t)k * SO));
+            kv[0] = v.x; kv[1] = v.y;
+        } else {
+#pragma unroll
+            for (int c = 0; c < R; c += 4) {
+                float4 v;
+                if constexpr (KS) v = *reinterpret_cast<const float4 *>(ko + (size_t)k * SO + c);
+                else v = __ldg(reinterpret_cast<const float4 *>(ko + (size_t)k * SO + c));
+                kv[c] = v.x; kv[c + 1] = v.y; kv[c + 2] = v.z; kv[c + 3] = v.w;
+            }
+        }
+        const float4 xa = xa_rows[k];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            y1[r][0] = fmaf(kv[r], xa.x, y1[r][0]);
+            y1[r][1] = fmaf(kv[r], xa.y, y1[r][1]);
+            y1[r][2] = fmaf(kv[r], xa.z, y1[r][2]);
+        }
+    }
+    unsigned any = 0u;
+#pragma unroll
+    for (int r = 0; r < R; ++r) any |= nz[r];
+    while (any) {                                   // warp-uniform: ascending lane, then ascending r = ascending k
+        const int l = __ffs(any) - 1;
+        any &= any - 1;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if ((nz[r] >> l) & 1u) {
+                const int k = l * R + r;
+                const float4 xb = xb_rows[k];
+                const float *col = kd + (size_t)k * SD + R;
+#pragma unroll
+                for (int q = 0; q < R; ++q) {
+                    const float dv = KS ? col[q] : __ldg(col + q);
+                    y2[q][0] = fmaf(dv, xb.x, y2[q][0]);
+                    y2[q][1] = fmaf(dv, xb.y, y2[q][1]);
+                    y2[q][2] = fmaf(dv, xb.z, y2[q][2]);
+                }
+            }
         }
     }
 }
@@ -341,7 +396,7 @@ __device__ __forceinline__ void cost_phase(const DevParams &p, const float2 *__r
 // ---------------------------------------------------------------------------
 template <int LPT, int R>
 __device__ __forceinline__ void grad_phase(const DevParams &p, const Group<LPT> &G, const Rows<R> &Rw, float lam_sg, float lam_jl,
-                                           float4 *XA, float4 *XB, bool commit)
+                                           float4 *XA, float4 *XB, bool commit, unsigned (&nz)[R])
 {
     const int T = p.T;
 #pragma unroll
@@ -371,10 +426,14 @@ __device__ __forceinline__ void grad_phase(const DevParams &p, const Group<LPT> 
             gq[k] = fmaf(lam_jl, jpg, fmaf(lam_sg, sgp, tg));
             gv[k] = fmaf(lam_jl, jvg, lam_sg * sgv);
         }
-        if (commit && t < T) {
+        const bool write = commit && t < T;
+        if (write) {
             XA[t] = make_float4(gq[0], gq[1], gq[2], 0.0f);
             XB[t] = make_float4(-gv[0], -gv[1], -gv[2], 0.0f);
         }
+        // rows whose velocity-gradient is not identically zero (consumed by contract_back)
+        const unsigned m = __ballot_sync(FULL, write && (gv[0] != 0.0f || gv[1] != 0.0f || gv[2] != 0.0f));
+        if (commit) nz[r] = m;
     }
 }
 

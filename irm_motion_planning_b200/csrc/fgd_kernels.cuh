@@ -20,13 +20,13 @@ namespace fgd {
 
 // shared-memory carve-up, identical on host and device
 struct SmemLayout {
-    int k_floats;     // floats of staged K (and dK), 0 when K stays in L2
+    int k_floats;     // T*TP when the K tables are staged in shared memory (KD = 2x, KO = 1x), 0 when they stay in L2
     int obs_pairs;    // obstacle slots (padded to even)
     int x_rows;       // float4 rows per operand buffer
     int n_groups;     // trajectory groups per CTA
     __host__ __device__ size_t bytes() const
     {
-        return (size_t)2 * k_floats * 4 + (size_t)obs_pairs * 8 + (size_t)n_groups * 2 * x_rows * 16 + (size_t)n_groups * sizeof(Slot);
+        return (size_t)3 * k_floats * 4 + (size_t)obs_pairs * 8 + (size_t)n_groups * 2 * x_rows * 16;
     }
 };
 
@@ -155,17 +155,18 @@ __device__ __forceinline__ void fetch_slot(const DevParams &p, const Group<LPT> 
 }
 
 template <bool KS>
-__device__ __forceinline__ void stage_constants(const DevParams &p, const SmemLayout &L, float *sK, float *sdK, float2 *sObs, int nthreads)
+__device__ __forceinline__ void stage_constants(const DevParams &p, const SmemLayout &L, float *sKD, float *sKO, float2 *sObs, int nthreads)
 {
     // trip counts are CTA-uniform (the bound check is inside), so no warp diverges ahead of the barrier
     if constexpr (KS) {
-        const float4 *gK = reinterpret_cast<const float4 *>(p.Kt), *gD = reinterpret_cast<const float4 *>(p.dKt);
-        float4 *dK4 = reinterpret_cast<float4 *>(sK), *dD4 = reinterpret_cast<float4 *>(sdK);
-        const int n4 = L.k_floats / 4;
+        const float4 *g4 = reinterpret_cast<const float4 *>(p.KD), *o4 = reinterpret_cast<const float4 *>(p.KO);
+        float4 *d4 = reinterpret_cast<float4 *>(sKD), *e4 = reinterpret_cast<float4 *>(sKO);
+        const int n4 = (2 * L.k_floats) / 4, m4 = L.k_floats / 4;
 #pragma unroll 1
         for (int i0 = 0; i0 < n4; i0 += nthreads) {
             const int i = i0 + threadIdx.x;
-            if (i < n4) { dK4[i] = __ldg(gK + i); dD4[i] = __ldg(gD + i); }
+            if (i < n4) d4[i] = __ldg(g4 + i);
+            if (i < m4) e4[i] = __ldg(o4 + i);
         }
     }
 #pragma unroll 1
@@ -187,23 +188,27 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int GPW = 32 / LPT;                    // groups (trajectories) per warp
-    const int T = p.T, TP = p.TP;
-    const SmemLayout L = make_layout(T, TP, p.n_obs, KS, NW * GPW);
-    float *sK = reinterpret_cast<float *>(smem_raw);
-    float *sdK = sK + L.k_floats;
-    float2 *sObs = reinterpret_cast<float2 *>(sdK + L.k_floats);
+    const int T = p.T;
+    const SmemLayout L = make_layout(T, LPT * R, p.n_obs, KS, NW * GPW);
+    float *sKD = reinterpret_cast<float *>(smem_raw);
+    float *sKO = sKD + 2 * L.k_floats;
+    float2 *sObs = reinterpret_cast<float2 *>(sKO + L.k_floats);
     float4 *sX = reinterpret_cast<float4 *>(sObs + L.obs_pairs);
-    Slot *sSlot = reinterpret_cast<Slot *>(sX + (size_t)L.n_groups * 2 * L.x_rows);
-    stage_constants<KS>(p, L, sK, sdK, sObs, NW * 32);
+    stage_constants<KS>(p, L, sKD, sKO, sObs, NW * 32);
 
     const Group<LPT> G;
     const int warp = threadIdx.x >> 5;
     const int gidx = warp * GPW + (G.lane / LPT);
-    const float *kp = (KS ? sK : p.Kt) + G.gl * R, *dp = (KS ? sdK : p.dKt) + G.gl * R;
+    const float *kd = (KS ? sKD : p.KD) + G.gl * 2 * R;
+    const float *ko = (KS ? sKO : p.KO) + G.gl * R;
     float4 *XA = sX + (size_t)(gidx * 2) * L.x_rows, *XB = XA + L.x_rows;
-    Slot *slot = sSlot + gidx;
 
     int kind = K_IDLE;
+    Slot st;                   // warp-uniform loop state of this warp's trajectory (registers)
+    st.traj = -1;
+    unsigned nz[R];            // non-zero rows of the velocity gradient operand (see contract_back)
+#pragma unroll
+    for (int r = 0; r < R; ++r) nz[r] = 0u;
     float a[R][3];     // alpha rows of this lane
     float d[R][3];     // step direction rows (normalised gradient for BLS, gradient for GD)
 #pragma unroll
@@ -215,15 +220,11 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
         float y1[R][3], y2[R][3];
         if (!boot) {
             if (!__any_sync(FULL, kind != K_IDLE)) break;
-            const float4 *x1 = XA, *x2 = (kind == K_BACK) ? XB : XA;
             __syncwarp();
-            contract<R, KS>(kp, dp, T, TP, x1, x2, y1, y2);
+            if (kind != K_BACK) contract<LPT, R, KS, true>(kd, T, XA, XA, y1, y2);       // forward: K x, dK x
+            else contract_back<LPT, R, KS>(ko, kd, T, XA, XB, nz, y1, y2);               // backward: K G_q + dK (-G_v)
             __syncwarp();
         }
-        // Group-uniform scalars live in a register copy of the slot; all lanes of a group compute and
-        // write back identical values.  Both groups of the warp run the same instruction stream; the
-        // per-group state only decides what gets committed.
-        Slot st = *slot;
         TRACE("lane %d trip boot=%d kind=%d\n", threadIdx.x, (int)boot, kind);
         const bool is_back = !boot && kind == K_BACK;
         const bool is_fwd = !boot && (kind == K_EVAL0 || kind == K_CAND);
@@ -311,7 +312,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
                 }
             }
             __syncwarp();
-            if (__any_sync(FULL, accept)) grad_phase<LPT, R>(p, G, Rw, st.lam_sg, st.lam_jl, XA, XB, accept);
+            if (__any_sync(FULL, accept)) grad_phase<LPT, R>(p, G, Rw, st.lam_sg, st.lam_jl, XA, XB, accept, nz);
         }
         // ---- common tail: loop heads, retirement, refill -------------------------------------
         bool save_active = false;
@@ -349,7 +350,6 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
         TRACE("lane %d after fetch kind=%d traj=%d\n", threadIdx.x, kind, st.traj);
         if (want_eval) begin_outer_eval<LPT, R>(p, G, st, kind, a, XA);
         if (want_cand) write_candidate<LPT, R>(p, G, st.lr, a, d, XA);
-        *slot = st;
         boot = false;
     }
 }
@@ -363,20 +363,20 @@ __global__ void __launch_bounds__(NW * 32) fgd_eval_kernel(const __grid_constant
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int GPW = 32 / LPT;
-    const int T = p.T, TP = p.TP;
-    const SmemLayout L = make_layout(T, TP, p.n_obs, KS, NW * GPW);
-    float *sK = reinterpret_cast<float *>(smem_raw);
-    float *sdK = sK + L.k_floats;
-    float2 *sObs = reinterpret_cast<float2 *>(sdK + L.k_floats);
+    const int T = p.T;
+    const SmemLayout L = make_layout(T, LPT * R, p.n_obs, KS, NW * GPW);
+    float *sKD = reinterpret_cast<float *>(smem_raw);
+    float *sKO = sKD + 2 * L.k_floats;
+    float2 *sObs = reinterpret_cast<float2 *>(sKO + L.k_floats);
     float4 *sX = reinterpret_cast<float4 *>(sObs + L.obs_pairs);
     MARK(1);
-    stage_constants<KS>(p, L, sK, sdK, sObs, NW * 32);
+    stage_constants<KS>(p, L, sKD, sKO, sObs, NW * 32);
     MARK(2);
 
     const Group<LPT> G;
     const int warp = threadIdx.x >> 5;
     const int gidx = warp * GPW + (G.lane / LPT);
-    const float *kp = (KS ? sK : p.Kt) + G.gl * R, *dp = (KS ? sdK : p.dKt) + G.gl * R;
+    const float *kd = (KS ? sKD : p.KD) + G.gl * 2 * R;
     float4 *XA = sX + (size_t)(gidx * 2) * L.x_rows, *XB = XA + L.x_rows;
     const int stride = gridDim.x * NW * GPW;
     const int n_rounds = (p.B + stride - 1) / stride;
@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(NW * 32) fgd_eval_kernel(const __grid_constant
         float y1[R][3], y2[R][3];
         MARK(3);
         __syncwarp();
-        contract<R, KS>(kp, dp, T, TP, XA, XA, y1, y2);
+        contract<LPT, R, KS, true>(kd, T, XA, XA, y1, y2);
         MARK(4);
         __syncwarp();
         {
@@ -430,11 +430,12 @@ __global__ void __launch_bounds__(NW * 32) fgd_eval_kernel(const __grid_constant
                     }
                 }
             }
-            if (e.grad) grad_phase<LPT, R>(p, G, Rw, e.lam_sg, e.lam_jl, XA, XB, live);
+            unsigned nz_unused[R];
+            if (e.grad) grad_phase<LPT, R>(p, G, Rw, e.lam_sg, e.lam_jl, XA, XB, live, nz_unused);
         }
         if (e.grad) {
             __syncwarp();
-            contract<R, KS>(kp, dp, T, TP, XA, XB, y1, y2);
+            contract<LPT, R, KS, false>(kd, T, XA, XB, y1, y2);
             if (live) {
                 float g[R][3];
                 backward_rows<R>(p, y1, y2, g);

@@ -102,7 +102,9 @@ def cpu_baseline(wl, traj, alpha0, start, goal, seconds, threads=0):
     sample of the same workload."""
     from oracle import mirror as M
     m = M.Mirror(hp_view(wl.args, traj.N_timesteps), traj.km, traj.dkm, traj.jac, wl.obstacles, wl.mode)
-    cores = M.max_threads() if threads <= 0 else threads
+    if threads <= 0:      # all host threads this process may use (torchrun pins OMP_NUM_THREADS=1, so ask the OS)
+        threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    cores = threads
     n0 = min(len(alpha0), max(cores * 2, 16))
     t = time.perf_counter()
     m.optimize(alpha0[:n0], start[:n0], goal[:n0], nthreads=threads)
@@ -342,7 +344,7 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": 1e3 * total_s / a.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_dict(wl, traj, B, trajectories_per_warp=h.launch_geometry(B)["trajectories_per_warp"],
+            "config": config_dict(wl, traj, B, launch=h.launch_geometry(B),
                                   math="strict" if a.strict_math else "fast (rcp.approx)"),
             "fgd_iters_per_s": n_iter_all * a.steps / total_s,
             "mean_inner_iters": float(inner.mean()), "fulfilled_frac": float(is_[:, backend.I_FULFILLED].mean()),

@@ -46,26 +46,28 @@ struct Geometry { int gpw, grid, block, smem; };
 struct Mapping { int LPT, R; };
 inline Mapping mapping_for(int T) { return T <= 64 ? Mapping{32, 2} : (T <= 128 ? Mapping{32, 4} : Mapping{32, 8}); }
 
-// (variant, LPT, R, KS, NW, MINB): the instantiated kernels.  NW warps per CTA, MINB = min CTAs per SM
-// (register cap).  Variant 0 is the default; the others exist for tuning (env FGD_VARIANT).
+// (variant, LPT, R, KS, NW, MINB, LEAN): the instantiated kernels.  KS: K tables staged in shared memory
+// (T <= 64) or read from L2; NW warps per CTA, MINB = min CTAs per SM (register cap); LEAN: alpha/direction
+// rows in shared memory and kinematics recomputed in the gradient phase (large T).  Variant 0 is the default;
+// the others exist for tuning (env FGD_VARIANT).
 #define FGD_FOR_CONFIGS(X) \
-    X(0, 32, 2, true, 8, 2) X(0, 32, 4, true, 4, 3) X(0, 32, 8, false, 4, 2) \
-    X(1, 32, 2, true, 4, 4) X(2, 32, 2, true, 16, 1)
+    X(0, 32, 2, true, 8, 2, false) X(0, 32, 4, false, 4, 4, true) X(0, 32, 8, false, 4, 2, true) \
+    X(1, 32, 2, true, 4, 4, false) X(1, 32, 8, false, 4, 3, true) X(2, 32, 8, false, 8, 1, true)
 
-template <int LPT, int R, bool STRICT, bool KS, int NW, int MINB>
+template <int LPT, int R, bool STRICT, bool KS, int NW, int MINB, bool LEAN>
 cudaError_t launch_opt(const DevParams &p, int grid, size_t smem, cudaStream_t st)
 {
-    auto kern = fgd_optimize_kernel<LPT, R, STRICT, KS, NW, MINB>;
+    auto kern = fgd_optimize_kernel<LPT, R, STRICT, KS, NW, MINB, LEAN>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, NW * 32, smem, st>>>(p);
     return cudaGetLastError();
 }
 
-template <int LPT, int R, bool STRICT, bool KS, int NW, int MINB>
+template <int LPT, int R, bool STRICT, bool KS, int NW, int MINB, bool LEAN>
 int occupancy_opt(size_t smem)
 {
-    auto kern = fgd_optimize_kernel<LPT, R, STRICT, KS, NW, MINB>;
+    auto kern = fgd_optimize_kernel<LPT, R, STRICT, KS, NW, MINB, LEAN>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int nb = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, NW * 32, smem) != cudaSuccess) nb = 1;
@@ -86,7 +88,7 @@ int g_variant = 0;
 
 bool variant_exists(int v, int LPT, int R)
 {
-#define X(V_, L_, R_, KS_, NW_, MB_) if (v == V_ && LPT == L_ && R == R_) return true;
+#define X(V_, L_, R_, KS_, NW_, MB_, LN_) if (v == V_ && LPT == L_ && R == R_) return true;
     FGD_FOR_CONFIGS(X)
 #undef X
     return false;
@@ -94,7 +96,7 @@ bool variant_exists(int v, int LPT, int R)
 
 int warps_per_cta(int v, int LPT, int R)
 {
-#define X(V_, L_, R_, KS_, NW_, MB_) if (v == V_ && LPT == L_ && R == R_) return NW_;
+#define X(V_, L_, R_, KS_, NW_, MB_, LN_) if (v == V_ && LPT == L_ && R == R_) return NW_;
     FGD_FOR_CONFIGS(X)
 #undef X
     return 4;
@@ -102,10 +104,10 @@ int warps_per_cta(int v, int LPT, int R)
 
 cudaError_t dispatch_opt(int v, int LPT, int R, bool strict, const DevParams &p, int grid, size_t smem, cudaStream_t st)
 {
-#define X(V_, L_, R_, KS_, NW_, MB_)                                                         \
+#define X(V_, L_, R_, KS_, NW_, MB_, LN_)                                                    \
     if (v == V_ && LPT == L_ && R == R_)                                                      \
-        return strict ? launch_opt<L_, R_, true, KS_, NW_, MB_>(p, grid, smem, st)            \
-                      : launch_opt<L_, R_, false, KS_, NW_, MB_>(p, grid, smem, st);
+        return strict ? launch_opt<L_, R_, true, KS_, NW_, MB_, LN_>(p, grid, smem, st)       \
+                      : launch_opt<L_, R_, false, KS_, NW_, MB_, LN_>(p, grid, smem, st);
     FGD_FOR_CONFIGS(X)
 #undef X
     return cudaErrorInvalidValue;
@@ -113,9 +115,9 @@ cudaError_t dispatch_opt(int v, int LPT, int R, bool strict, const DevParams &p,
 
 int dispatch_occ(int v, int LPT, int R, bool strict, size_t smem)
 {
-#define X(V_, L_, R_, KS_, NW_, MB_)                                                         \
+#define X(V_, L_, R_, KS_, NW_, MB_, LN_)                                                    \
     if (v == V_ && LPT == L_ && R == R_)                                                      \
-        return strict ? occupancy_opt<L_, R_, true, KS_, NW_, MB_>(smem) : occupancy_opt<L_, R_, false, KS_, NW_, MB_>(smem);
+        return strict ? occupancy_opt<L_, R_, true, KS_, NW_, MB_, LN_>(smem) : occupancy_opt<L_, R_, false, KS_, NW_, MB_, LN_>(smem);
     FGD_FOR_CONFIGS(X)
 #undef X
     return 1;
@@ -123,7 +125,7 @@ int dispatch_occ(int v, int LPT, int R, bool strict, size_t smem)
 
 cudaError_t dispatch_eval(int LPT, int R, bool strict, const DevParams &p, const EvalPtrs &e, int grid, size_t smem, cudaStream_t st)
 {
-#define X(V_, L_, R_, KS_, NW_, MB_)                                                         \
+#define X(V_, L_, R_, KS_, NW_, MB_, LN_)                                                    \
     if (V_ == 0 && LPT == L_ && R == R_)                                                      \
         return strict ? launch_eval<L_, R_, true, KS_, NW_>(p, e, grid, smem, st)             \
                       : launch_eval<L_, R_, false, KS_, NW_>(p, e, grid, smem, st);
@@ -138,7 +140,7 @@ Geometry geometry(const FgdHandle *h, int B, int n_obs)
     const int nw = warps_per_cta(h->variant, h->LPT, h->R);
     g.gpw = 32 / h->LPT;
     g.block = nw * 32;
-    g.smem = (int)make_layout(h->T, h->TP, n_obs, h->k_in_smem, nw * g.gpw).bytes();
+    g.smem = (int)make_layout(h->T, h->TP, n_obs, h->k_in_smem, nw * g.gpw, h->R > 2).bytes();
     const int occ = dispatch_occ(h->variant, h->LPT, h->R, h->cfg.strict_math != 0, (size_t)g.smem);
     const long long per_cta = (long long)nw * g.gpw;
     const long long need = ((long long)B + per_cta - 1) / per_cta;
@@ -244,7 +246,7 @@ int fgd_create(const FgdConfig *cfg, FgdHandle **out)
     CKC(cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
     // K and dK go to shared memory when both fit beside the operand buffers of at least one slot per warp
     if (const char *e = std::getenv("FGD_VARIANT")) { const int v = std::atoi(e); if (variant_exists(v, h->LPT, h->R)) h->variant = v; }
-    h->k_in_smem = h->R <= 4;     // T <= 128: 2*T*TP*4 B <= 128 KB; T = 256 streams K rows from L2
+    h->k_in_smem = h->R == 2;     // T <= 64: 3*T*64*4 B <= 48 KB per CTA; larger T reads the K tables from L2
 
     // operand table KD[k][lane][2R]: the R row entries K[t][k] then the R entries dK[t][k] of lane's rows t = R*lane + r
     // and KO[k][lane][R]: the K entries alone (dense half of the backward contraction)
@@ -353,7 +355,7 @@ int fgd_eval_cost_grad(FgdHandle *h, int32_t B, const float *d_alpha, const floa
     }
     EvalPtrs e{lambda_sg, lambda_jl, d_loss, d_toc, d_grad, d_q, d_v, d_fulfilled};
     const int nw = warps_per_cta(0, h->LPT, h->R), per_cta = nw * (32 / h->LPT);
-    const size_t smem = make_layout(h->T, h->TP, p.n_obs, h->k_in_smem, per_cta).bytes();
+    const size_t smem = make_layout(h->T, h->TP, p.n_obs, h->k_in_smem, per_cta, false).bytes();
     long long need = ((long long)B + per_cta - 1) / per_cta, cap = (long long)h->num_sms * 4;
     const int grid = (int)(need < cap ? need : cap);
     CK(dispatch_eval(h->LPT, h->R, h->cfg.strict_math != 0, p, e, grid, smem, st));

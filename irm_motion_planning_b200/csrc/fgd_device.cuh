@@ -173,12 +173,13 @@ __device__ __forceinline__ void contract(const float *__restrict__ kd, int T,
                                          float (&y1)[R][3], float (&y2)[R][3])
 {
     constexpr int STRIDE = 2 * LPT * R;       // floats per column k
+    constexpr int UNROLL = (R >= 8) ? 2 : ((R == 4) ? 3 : 5);
 #pragma unroll
     for (int r = 0; r < R; ++r)
 #pragma unroll
         for (int a = 0; a < 3; ++a) { y1[r][a] = 0.0f; y2[r][a] = 0.0f; }
 
-#pragma unroll 5
+#pragma unroll UNROLL
     for (int k = 0; k < T; ++k) {
         float kv[2 * R];
 #pragma unroll
@@ -217,11 +218,12 @@ __device__ __forceinline__ void contract_back(const float *__restrict__ ko, cons
                                               const unsigned (&nz)[R], float (&y1)[R][3], float (&y2)[R][3])
 {
     constexpr int SO = LPT * R, SD = 2 * LPT * R;
+    constexpr int UNROLL = (R >= 8) ? 2 : ((R == 4) ? 3 : 5);
 #pragma unroll
     for (int r = 0; r < R; ++r)
 #pragma unroll
         for (int a = 0; a < 3; ++a) { y1[r][a] = 0.0f; y2[r][a] = 0.0f; }
-#pragma unroll 5
+#pragma unroll UNROLL
     for (int k = 0; k < T; ++k) {
         float kv[R];
         if constexpr (R == 2) {
@@ -270,13 +272,31 @@ __device__ __forceinline__ void contract_back(const float *__restrict__ ko, cons
     }
 }
 
-// Per-lane rows kept between the cost phase and the gradient phase.
-template <int R>
+// Per-lane rows kept between the cost phase and the gradient phase.  LEAN variants (R >= 4)
+// keep only the obstacle gradient and recompute q, v and the sines/cosines in the gradient
+// phase from the contraction rows (same arithmetic, same bits) to stay out of the spill zone.
+template <int R, bool LEAN>
 struct Rows {
-    float q[R][3], v[R][3], sn[R][3], cs[R][3], gx[R], gy[R];
-    float d0[3], dT[3];   // q[0]-start, q[T-1]-goal (meaningful in the owning lanes)
+    float q[LEAN ? 1 : R][3], v[LEAN ? 1 : R][3], sn[LEAN ? 1 : R][3], cs[LEAN ? 1 : R][3];
+    float gx[R], gy[R];
     int amax;
 };
+
+// q, v rows from the raw contraction rows ((M @ alpha) @ J, trajectory.py:65) and the
+// sines / cosines of the cumulative joint angles (robot.py:32).
+__device__ __forceinline__ void row_kinematics(const DevParams &p, const float (&yq)[3], const float (&yv)[3],
+                                               float (&q)[3], float (&v)[3], float (&sn)[3], float (&cs)[3])
+{
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+        q[b] = fmaf(yq[2], p.J[6 + b], fmaf(yq[1], p.J[3 + b], yq[0] * p.J[b]));
+        v[b] = fmaf(yv[2], p.J[6 + b], fmaf(yv[1], p.J[3 + b], yv[0] * p.J[b]));
+    }
+    const float c1 = q[0], c2 = c1 + q[1], c3 = c2 + q[2];
+    sincos_cw(c1, sn[0], cs[0]);
+    sincos_cw(c2, sn[1], cs[1]);
+    sincos_cw(c3, sn[2], cs[2]);
+}
 
 // ---------------------------------------------------------------------------
 // Cost phase: compute_trajectory_cost + constraintsFulfilled for one trajectory
@@ -287,38 +307,66 @@ struct Rows {
 // The obstacle loop accumulates sum 1/den and sum d/den^2; the constant factors
 // 0.8 and -0.8 of environment.py:43,57 are applied once per sample.
 // ---------------------------------------------------------------------------
-template <int LPT, int R, bool STRICT>
+template <int LPT, int R, bool STRICT, bool LEAN>
 __device__ __forceinline__ void cost_phase(const DevParams &p, const float2 *__restrict__ sObs, const Group<LPT> &G,
                                            const float (&yq)[R][3], const float (&yv)[R][3],
                                            const float *start, const float *goal, float lam_sg, float lam_jl,
-                                           Rows<R> &Rw, float &loss, float &toc, int &ful)
+                                           Rows<R, LEAN> &Rw, float &loss, float &toc, int &ful)
 {
     const int T = p.T;
     const int t0 = G.gl * R;
-    float cost[R];
+    const int lT = (T - 1) / R, rT = (T - 1) % R;
     float part_c = 0.0f, part_p = 0.0f, part_v = 0.0f, lmax = 0.0f;
     bool lim_ok = true;
     float x[R], y[R], sr[R], sx[R], sy[R];
+    float ssp0 = 0.0f, ssv0 = 0.0f, sspT = 0.0f, ssvT = 0.0f;      // meaningful in the lanes owning rows 0 / T-1
 #pragma unroll
     for (int r = 0; r < R; ++r) {
+        const bool valid = (t0 + r) < T;
+        float q[3], v[3], sn[3], cs[3];
+        row_kinematics(p, yq[r], yv[r], q, v, sn, cs);
+        if constexpr (!LEAN) {
 #pragma unroll
-        for (int b = 0; b < 3; ++b) {   // (M @ alpha) @ J
-            Rw.q[r][b] = fmaf(yq[r][2], p.J[6 + b], fmaf(yq[r][1], p.J[3 + b], yq[r][0] * p.J[b]));
-            Rw.v[r][b] = fmaf(yv[r][2], p.J[6 + b], fmaf(yv[r][1], p.J[3 + b], yv[r][0] * p.J[b]));
+            for (int b = 0; b < 3; ++b) { Rw.q[r][b] = q[b]; Rw.v[r][b] = v[b]; Rw.sn[r][b] = sn[b]; Rw.cs[r][b] = cs[b]; }
         }
-        const float c1 = Rw.q[r][0], c2 = c1 + Rw.q[r][1], c3 = c2 + Rw.q[r][2];
-        sincos_cw(c1, Rw.sn[r][0], Rw.cs[r][0]);
-        sincos_cw(c2, Rw.sn[r][1], Rw.cs[r][1]);
-        sincos_cw(c3, Rw.sn[r][2], Rw.cs[r][2]);
-        x[r] = fmaf(p.link[2], Rw.cs[r][2], fmaf(p.link[1], Rw.cs[r][1], p.link[0] * Rw.cs[r][0]));
-        y[r] = fmaf(p.link[2], Rw.sn[r][2], fmaf(p.link[1], Rw.sn[r][1], p.link[0] * Rw.sn[r][0]));
+        x[r] = fmaf(p.link[2], cs[2], fmaf(p.link[1], cs[1], p.link[0] * cs[0]));     // robot.py:33
+        y[r] = fmaf(p.link[2], sn[2], fmaf(p.link[1], sn[1], p.link[0] * sn[0]));     // robot.py:34
         sr[r] = 0.0f; sx[r] = 0.0f; sy[r] = 0.0f;
+        // joint-limit penalties and limit predicates of this row   trajectory.py:215-255, robot.py:104-113
+        float e3[3], f3[3];
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            const float qb = q[b], vb = v[b];
+            const float u = (qb - p.mean_q) * p.inv_std;
+            const bool m = p.cvdl ? (qb > p.q_hi || qb < p.q_lo) : true;
+            e3[b] = m ? 0.5f * (u * u) : 0.0f;
+            const float w = vb * p.inv_vmax;
+            const bool mv = p.cvdl ? (fabsf(vb) > p.v_hi) : true;
+            f3[b] = mv ? 0.5f * (w * w) : 0.0f;
+            lim_ok = lim_ok & (!valid | ((qb <= p.qmax) & (qb >= p.qmin) & (fabsf(vb) <= p.vmax)));
+        }
+        if (valid) {
+            part_p = part_p + ((e3[0] + e3[1]) + e3[2]);
+            part_v = part_v + ((f3[0] + f3[1]) + f3[2]);
+        }
+        // start / goal rows   trajectory.py:183-204
+        if (r == 0) {
+            ssp0 = ss3(q[0] - start[0], q[1] - start[1], q[2] - start[2]);
+            ssv0 = ss3(v[0], v[1], v[2]);
+        }
+        if (r == rT) {
+            sspT = ss3(q[0] - goal[0], q[1] - goal[1], q[2] - goal[2]);
+            ssvT = ss3(v[0], v[1], v[2]);
+        }
     }
     // obstacle potential: all R samples of this lane against every obstacle
     const int n_obs = p.n_obs;
-#pragma unroll 2
+    constexpr int OBS_UNROLL = (R >= 8) ? 1 : 2;      // R independent chains per obstacle already
+    float2 ob_next = sObs[0];                       // software pipelining: the next obstacle is fetched one trip ahead
+#pragma unroll OBS_UNROLL
     for (int o = 0; o < n_obs; ++o) {
-        const float2 ob = sObs[o];
+        const float2 ob = ob_next;
+        ob_next = sObs[o + 1];                      // the buffer is padded by one pair (make_layout)
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const float dx = x[r] - ob.x, dy = y[r] - ob.y;
@@ -331,27 +379,13 @@ __device__ __forceinline__ void cost_phase(const DevParams &p, const float2 *__r
             sy[r] = fmaf(r2, dy, sy[r]);
         }
     }
+    float cost[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        const bool valid = (t0 + r) < T;
         const float c = 0.8f * sr[r];
         cost[r] = c; Rw.gx[r] = -0.8f * sx[r]; Rw.gy[r] = -0.8f * sy[r];
-        float e3[3], f3[3];
-#pragma unroll
-        for (int b = 0; b < 3; ++b) {
-            const float qb = Rw.q[r][b], vb = Rw.v[r][b];
-            const float u = (qb - p.mean_q) * p.inv_std;
-            const bool m = p.cvdl ? (qb > p.q_hi || qb < p.q_lo) : true;
-            e3[b] = m ? 0.5f * (u * u) : 0.0f;
-            const float w = vb * p.inv_vmax;
-            const bool mv = p.cvdl ? (fabsf(vb) > p.v_hi) : true;
-            f3[b] = mv ? 0.5f * (w * w) : 0.0f;
-            lim_ok = lim_ok & (!valid | ((qb <= p.qmax) & (qb >= p.qmin) & (fabsf(vb) <= p.vmax)));
-        }
-        if (valid) {
+        if ((t0 + r) < T) {
             part_c = part_c + c;
-            part_p = part_p + ((e3[0] + e3[1]) + e3[2]);
-            part_v = part_v + ((f3[0] + f3[1]) + f3[2]);
             lmax = fmaxf(lmax, c);          // c >= 0
         }
     }
@@ -365,21 +399,10 @@ __device__ __forceinline__ void cost_phase(const DevParams &p, const float2 *__r
     const float avg = gsum<LPT>(part_c) / p.fT;
     toc = fmaf(p.lam_max, maxc, p.oml * avg);
 
-    // start / goal rows
-    const int lT = (T - 1) / R, rT = (T - 1) % R;
-    float qT[3] = {0.f, 0.f, 0.f}, vT[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-    for (int r = 0; r < R; ++r)
-        if (r == rT) {
-#pragma unroll
-            for (int b = 0; b < 3; ++b) { qT[b] = Rw.q[r][b]; vT[b] = Rw.v[r][b]; }
-        }
-#pragma unroll
-    for (int b = 0; b < 3; ++b) { Rw.d0[b] = Rw.q[0][b] - start[b]; Rw.dT[b] = qT[b] - goal[b]; }
-    const float ssp0 = gbcast<LPT>(ss3(Rw.d0[0], Rw.d0[1], Rw.d0[2]), 0);
-    const float ssv0 = gbcast<LPT>(ss3(Rw.v[0][0], Rw.v[0][1], Rw.v[0][2]), 0);
-    const float sspT = gbcast<LPT>(ss3(Rw.dT[0], Rw.dT[1], Rw.dT[2]), lT);
-    const float ssvT = gbcast<LPT>(ss3(vT[0], vT[1], vT[2]), lT);
+    ssp0 = gbcast<LPT>(ssp0, 0);
+    ssv0 = gbcast<LPT>(ssv0, 0);
+    sspT = gbcast<LPT>(sspT, lT);
+    ssvT = gbcast<LPT>(ssvT, lT);
     const float sg = (0.5f * ssp0 + 0.5f * sspT) + (0.5f * ssv0 + 0.5f * ssvT);
     const float jl = gsum<LPT>(part_p) / p.fT + gsum<LPT>(part_v) / p.fT;
     loss = fmaf(lam_jl, jl, fmaf(lam_sg, sg, toc));
@@ -392,21 +415,30 @@ __device__ __forceinline__ void cost_phase(const DevParams &p, const float2 *__r
 // Gradient phase: rows of  G_q = toc_g + lam_sg*sgp_g + lam_jl*jp_g  and
 // G_v = lam_sg*sgv_g + lam_jl*jv_g  (trajectory.py:289-295, :91-126, robot.py:75-87),
 // written as the operands of the backward contraction: XA = G_q, XB = -G_v
-// (dK^T = -dK bit-exactly, checked in fgd_create()).
+// (dK^T = -dK bit-exactly, checked in fgd_create()).  nz[r] collects the rows whose
+// velocity gradient is not identically zero (consumed by contract_back).
 // ---------------------------------------------------------------------------
-template <int LPT, int R>
-__device__ __forceinline__ void grad_phase(const DevParams &p, const Group<LPT> &G, const Rows<R> &Rw, float lam_sg, float lam_jl,
-                                           float4 *XA, float4 *XB, bool commit, unsigned (&nz)[R])
+template <int LPT, int R, bool LEAN>
+__device__ __forceinline__ void grad_phase(const DevParams &p, const Group<LPT> &G, const Rows<R, LEAN> &Rw,
+                                           const float (&yq)[R][3], const float (&yv)[R][3], const float *start, const float *goal,
+                                           float lam_sg, float lam_jl, float4 *XA, float4 *XB, bool commit, unsigned (&nz)[R])
 {
     const int T = p.T;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const int t = G.gl * R + r;
+        float q[3], v[3], sn[3], cs[3];
+        if constexpr (LEAN) {
+            row_kinematics(p, yq[r], yv[r], q, v, sn, cs);
+        } else {
+#pragma unroll
+            for (int b = 0; b < 3; ++b) { q[b] = Rw.q[r][b]; v[b] = Rw.v[r][b]; sn[b] = Rw.sn[r][b]; cs[b] = Rw.cs[r][b]; }
+        }
         const float wt = (t == Rw.amax) ? (p.lam_max + p.w_avg) : p.w_avg;
         const float cgx = wt * Rw.gx[r], cgy = wt * Rw.gy[r];
         float xs[3], ys[3];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) { xs[k] = -(p.link[k] * Rw.sn[r][k]); ys[k] = p.link[k] * Rw.cs[r][k]; }
+        for (int k = 0; k < 3; ++k) { xs[k] = -(p.link[k] * sn[k]); ys[k] = p.link[k] * cs[k]; }
         const float Sx = (xs[0] + xs[1]) + xs[2], Sy = (ys[0] + ys[1]) + ys[2];
         const float Cx[3] = {xs[0], xs[0] + xs[1], (xs[0] + xs[1]) + xs[2]};
         const float Cy[3] = {ys[0], ys[0] + ys[1], (ys[0] + ys[1]) + ys[2]};
@@ -416,8 +448,8 @@ __device__ __forceinline__ void grad_phase(const DevParams &p, const Group<LPT> 
             const float Jx = (xs[k] + Sx) - Cx[k];
             const float Jy = (ys[k] + Sy) - Cy[k];
             const float tg = fmaf(cgy, Jy, cgx * Jx);
-            const float qk = Rw.q[r][k], vk = Rw.v[r][k];
-            const float sgp = (t == 0) ? Rw.d0[k] : ((t == T - 1) ? Rw.dT[k] : 0.0f);
+            const float qk = q[k], vk = v[k];
+            const float sgp = (t == 0) ? (qk - start[k]) : ((t == T - 1) ? (qk - goal[k]) : 0.0f);
             const float sgv = (t == 0 || t == T - 1) ? vk : 0.0f;
             const bool m = p.cvdl ? (qk > p.q_hi || qk < p.q_lo) : true;
             const float jpg = m ? ((qk - p.mean_q) * p.inv_std2) * p.inv_T : 0.0f;
@@ -431,7 +463,6 @@ __device__ __forceinline__ void grad_phase(const DevParams &p, const Group<LPT> 
             XA[t] = make_float4(gq[0], gq[1], gq[2], 0.0f);
             XB[t] = make_float4(-gv[0], -gv[1], -gv[2], 0.0f);
         }
-        // rows whose velocity-gradient is not identically zero (consumed by contract_back)
         const unsigned m = __ballot_sync(FULL, write && (gv[0] != 0.0f || gv[1] != 0.0f || gv[2] != 0.0f));
         if (commit) nz[r] = m;
     }

@@ -23,21 +23,37 @@ struct SmemLayout {
     int k_floats;     // T*TP when the K tables are staged in shared memory (KD = 2x, KO = 1x), 0 when they stay in L2
     int obs_pairs;    // obstacle slots (padded to even)
     int x_rows;       // float4 rows per operand buffer
+    int ad_rows;      // float4 slots per alpha / direction buffer (LEAN variants keep them in shared memory, lane-major)
     int n_groups;     // trajectory groups per CTA
     __host__ __device__ size_t bytes() const
     {
-        return (size_t)3 * k_floats * 4 + (size_t)obs_pairs * 8 + (size_t)n_groups * 2 * x_rows * 16;
+        return (size_t)3 * k_floats * 4 + (size_t)obs_pairs * 8 + (size_t)n_groups * 2 * (x_rows + ad_rows) * 16;
     }
 };
 
-__host__ __device__ inline SmemLayout make_layout(int T, int TP, int n_obs, bool ks, int n_groups)
+__host__ __device__ inline SmemLayout make_layout(int T, int TP, int n_obs, bool ks, int n_groups, bool lean)
 {
     SmemLayout l;
     l.k_floats = ks ? T * TP : 0;
-    l.obs_pairs = (n_obs + 1) & ~1;
+    l.obs_pairs = (n_obs + 2) & ~1;     // >= n_obs + 1: the obstacle loop prefetches one pair ahead
     l.x_rows = T | 1;     // odd row count: the operand buffers of neighbouring groups start 4 banks apart (mod 8)
+    l.ad_rows = lean ? TP : 0;
     l.n_groups = n_groups;
     return l;
+}
+
+// lane-major row store: slot (r, lane) -> buf[r * 32 + lane]   (conflict-free for a warp)
+template <int R>
+__device__ __forceinline__ void ld_rows(const float4 *buf, int lane, float (&x)[R][3])
+{
+#pragma unroll
+    for (int r = 0; r < R; ++r) { const float4 v = buf[r * 32 + lane]; x[r][0] = v.x; x[r][1] = v.y; x[r][2] = v.z; }
+}
+template <int R>
+__device__ __forceinline__ void st_rows(float4 *buf, int lane, const float (&x)[R][3])
+{
+#pragma unroll
+    for (int r = 0; r < R; ++r) buf[r * 32 + lane] = make_float4(x[r][0], x[r][1], x[r][2], 0.0f);
 }
 
 __device__ __forceinline__ void hash_step(Slot &st, unsigned code) { st.hash = st.hash * 1000003u + code; }
@@ -170,9 +186,9 @@ __device__ __forceinline__ void stage_constants(const DevParams &p, const SmemLa
         }
     }
 #pragma unroll 1
-    for (int i0 = 0; i0 < p.n_obs; i0 += nthreads) {
+    for (int i0 = 0; i0 < L.obs_pairs; i0 += nthreads) {
         const int i = i0 + threadIdx.x;
-        if (i < p.n_obs) sObs[i] = make_float2(p.obs[2 * i], p.obs[2 * i + 1]);
+        if (i < L.obs_pairs) sObs[i] = (i < p.n_obs) ? make_float2(p.obs[2 * i], p.obs[2 * i + 1]) : make_float2(0.f, 0.f);
     }
     __syncthreads();
 }
@@ -183,13 +199,14 @@ __device__ __forceinline__ void stage_constants(const DevParams &p, const SmemLa
 // is empty.  One loop trip = one contraction (K loads shared by the groups of
 // the warp) + the group's post-processing (candidate evaluation or gradient).
 // ---------------------------------------------------------------------------
-template <int LPT, int R, bool STRICT, bool KS, int NW, int MINB>
+template <int LPT, int R, bool STRICT, bool KS, int NW, int MINB, bool LEAN>
 __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __grid_constant__ DevParams p)
 {
+    static_assert(!LEAN || LPT == 32, "LEAN variants are one warp per trajectory");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int GPW = 32 / LPT;                    // groups (trajectories) per warp
     const int T = p.T;
-    const SmemLayout L = make_layout(T, LPT * R, p.n_obs, KS, NW * GPW);
+    const SmemLayout L = make_layout(T, LPT * R, p.n_obs, KS, NW * GPW, LEAN);
     float *sKD = reinterpret_cast<float *>(smem_raw);
     float *sKO = sKD + 2 * L.k_floats;
     float2 *sObs = reinterpret_cast<float2 *>(sKO + L.k_floats);
@@ -201,7 +218,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
     const int gidx = warp * GPW + (G.lane / LPT);
     const float *kd = (KS ? sKD : p.KD) + G.gl * 2 * R;
     const float *ko = (KS ? sKO : p.KO) + G.gl * R;
-    float4 *XA = sX + (size_t)(gidx * 2) * L.x_rows, *XB = XA + L.x_rows;
+    float4 *XA = sX + (size_t)(gidx * 2) * (L.x_rows + L.ad_rows), *XB = XA + L.x_rows;
+    float4 *SA = XB + L.x_rows, *SD = SA + L.ad_rows;      // LEAN: alpha / direction rows, lane-major
 
     int kind = K_IDLE;
     Slot st;                   // warp-uniform loop state of this warp's trajectory (registers)
@@ -259,6 +277,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
                 for (int r = 0; r < R; ++r)
 #pragma unroll
                     for (int b = 0; b < 3; ++b) d[r][b] = g[r][b];
+                if constexpr (LEAN) st_rows<R>(SD, G.lane, d);
                 st.alpha_norm = alpha_norm; st.j = 0;
                 want_cand = true;
                 kind = K_CAND;
@@ -267,10 +286,10 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
         __syncwarp();
         if (__any_sync(FULL, is_fwd)) {
             // ---- loss (and, if accepted, gradient operands) at alpha or at a candidate -------
-            Rows<R> Rw;
+            Rows<R, LEAN> Rw;
             float loss_c, toc_c;
             int ful_c;
-            cost_phase<LPT, R, STRICT>(p, sObs, G, y1, y2, st.start, st.goal, st.lam_sg, st.lam_jl, Rw, loss_c, toc_c, ful_c);
+            cost_phase<LPT, R, STRICT, LEAN>(p, sObs, G, y1, y2, st.start, st.goal, st.lam_sg, st.lam_jl, Rw, loss_c, toc_c, ful_c);
             bool accept = false;
             if (is_fwd) {
                 if (kind == K_EVAL0) {
@@ -301,7 +320,9 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
                     } else if (p.mode == 1 && minimized) {
                         hash_step(st, 3u); want_end = true;    // GD: the candidate is discarded (optimizer_GD.py:191-192)
                     } else {
+                        if constexpr (LEAN) { ld_rows<R>(SA, G.lane, a); ld_rows<R>(SD, G.lane, d); }
                         accept_candidate<R>(p, lr, a, d);
+                        if constexpr (LEAN) st_rows<R>(SA, G.lane, a);
                         accept = true;
                         if (p.mode == 0) st.lr = lr * p.bls_bp;
                         st.accepts += 1; hash_step(st, 2u);
@@ -312,7 +333,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
                 }
             }
             __syncwarp();
-            if (__any_sync(FULL, accept)) grad_phase<LPT, R>(p, G, Rw, st.lam_sg, st.lam_jl, XA, XB, accept, nz);
+            if (__any_sync(FULL, accept))
+                grad_phase<LPT, R, LEAN>(p, G, Rw, y1, y2, st.start, st.goal, st.lam_sg, st.lam_jl, XA, XB, accept, nz);
         }
         // ---- common tail: loop heads, retirement, refill -------------------------------------
         bool save_active = false;
@@ -343,13 +365,25 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
         TRACE("lane %d tail head=%d end=%d refill=%d kind=%d\n", threadIdx.x, (int)want_head, (int)want_end, (int)refill, kind);
         __syncwarp();
         if (__any_sync(FULL, refill)) {
-            if (refill && !boot) save_slot<LPT, R>(p, G, st, retire ? FGD_ST_DONE : FGD_ST_ACTIVE, a);
+            if (refill && !boot) {
+                if constexpr (LEAN) ld_rows<R>(SA, G.lane, a);
+                save_slot<LPT, R>(p, G, st, retire ? FGD_ST_DONE : FGD_ST_ACTIVE, a);
+            }
             fetch_slot<LPT, R>(p, G, refill, st, kind, a);
-            if (refill) want_eval = (kind != K_IDLE);
+            if (refill) {
+                want_eval = (kind != K_IDLE);
+                if constexpr (LEAN) st_rows<R>(SA, G.lane, a);
+            }
         }
         TRACE("lane %d after fetch kind=%d traj=%d\n", threadIdx.x, kind, st.traj);
-        if (want_eval) begin_outer_eval<LPT, R>(p, G, st, kind, a, XA);
-        if (want_cand) write_candidate<LPT, R>(p, G, st.lr, a, d, XA);
+        if (want_eval) {
+            if constexpr (LEAN) ld_rows<R>(SA, G.lane, a);
+            begin_outer_eval<LPT, R>(p, G, st, kind, a, XA);
+        }
+        if (want_cand) {
+            if constexpr (LEAN) { ld_rows<R>(SA, G.lane, a); ld_rows<R>(SD, G.lane, d); }
+            write_candidate<LPT, R>(p, G, st.lr, a, d, XA);
+        }
         boot = false;
     }
 }
@@ -364,7 +398,7 @@ __global__ void __launch_bounds__(NW * 32) fgd_eval_kernel(const __grid_constant
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int GPW = 32 / LPT;
     const int T = p.T;
-    const SmemLayout L = make_layout(T, LPT * R, p.n_obs, KS, NW * GPW);
+    const SmemLayout L = make_layout(T, LPT * R, p.n_obs, KS, NW * GPW, false);
     float *sKD = reinterpret_cast<float *>(smem_raw);
     float *sKO = sKD + 2 * L.k_floats;
     float2 *sObs = reinterpret_cast<float2 *>(sKO + L.k_floats);
@@ -409,10 +443,11 @@ __global__ void __launch_bounds__(NW * 32) fgd_eval_kernel(const __grid_constant
         MARK(4);
         __syncwarp();
         {
-            Rows<R> Rw;
+            constexpr bool LEAN = (R > 2);
+            Rows<R, LEAN> Rw;
             float loss, toc;
             int ful;
-            cost_phase<LPT, R, STRICT>(p, sObs, G, y1, y2, start, goal, e.lam_sg, e.lam_jl, Rw, loss, toc, ful);
+            cost_phase<LPT, R, STRICT, LEAN>(p, sObs, G, y1, y2, start, goal, e.lam_sg, e.lam_jl, Rw, loss, toc, ful);
             MARK(5);
             if (live && G.gl == 0) {
                 if (e.loss) e.loss[b] = loss;
@@ -422,16 +457,18 @@ __global__ void __launch_bounds__(NW * 32) fgd_eval_kernel(const __grid_constant
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const int t = G.gl * R + r;
-                if (live && t < T) {
+                if (live && t < T && (e.q || e.v)) {
+                    float q[3], v[3], sn[3], cs[3];
+                    row_kinematics(p, y1[r], y2[r], q, v, sn, cs);
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
-                        if (e.q) e.q[((size_t)b * T + t) * 3 + k] = Rw.q[r][k];
-                        if (e.v) e.v[((size_t)b * T + t) * 3 + k] = Rw.v[r][k];
+                        if (e.q) e.q[((size_t)b * T + t) * 3 + k] = q[k];
+                        if (e.v) e.v[((size_t)b * T + t) * 3 + k] = v[k];
                     }
                 }
             }
             unsigned nz_unused[R];
-            if (e.grad) grad_phase<LPT, R>(p, G, Rw, e.lam_sg, e.lam_jl, XA, XB, live, nz_unused);
+            if (e.grad) grad_phase<LPT, R, LEAN>(p, G, Rw, y1, y2, start, goal, e.lam_sg, e.lam_jl, XA, XB, live, nz_unused);
         }
         if (e.grad) {
             __syncwarp();

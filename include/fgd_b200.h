@@ -146,6 +146,20 @@ int fgd_argmin_per_problem(FgdHandle *h, int32_t n_problems, int32_t n_restarts,
                            const int32_t *d_istate, int32_t index_offset, float *d_best_cost,
                            int32_t *d_best_index, void *stream);
 
+/* Trajectory.initTrajectory (trajectory.py:73-78) on the device, for sweeps whose
+ * start/goal already live in HBM.  The reference solves
+ * K alpha = line J^-1 per trajectory with line = start + c(t) (goal - start); the
+ * right-hand side has rank 2 in t, so
+ *     alpha[b][t][:] = u[t] * (start_b J^-1) + w[t] * ((goal_b - start_b) J^-1),
+ * with u = K^-1 1 and w = K^-1 c solved ONCE on the host (same FP32 LU) and
+ * passed in here.  Equal to the reference's init in exact arithmetic; in FP32 both
+ * are within the LU residual of the same line (K is numerically singular), so
+ * this is offered BESIDE the host init, never instead of it.
+ *   h_u, h_w [T], h_jinv [9] row-major: host arrays, copied.
+ *   fgd_init_trajectory: d_start/d_goal [B][3] -> d_alpha [B][T][3]. */
+int fgd_set_init_basis(FgdHandle *h, const float *h_u, const float *h_w, const float *h_jinv);
+int fgd_init_trajectory(FgdHandle *h, int32_t B, const float *d_start, const float *d_goal, float *d_alpha, void *stream);
+
 /* Introspection for the harness. */
 int fgd_launch_geometry(const FgdHandle *h, int32_t B, int32_t *grid, int32_t *block, int32_t *smem_bytes,
                         int32_t *trajectories_per_warp);

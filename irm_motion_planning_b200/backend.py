@@ -49,7 +49,7 @@ EXPORTED_SYMBOLS = (
     "fgd_create", "fgd_destroy", "fgd_status_string", "fgd_last_cuda_error", "fgd_set_obstacles_async",
     "fgd_obstacle_count", "fgd_eval_cost_grad", "fgd_optimize_bls", "fgd_optimize_gd", "fgd_optimize_host",
     "fgd_argmin_per_problem", "fgd_launch_geometry", "fgd_kernel_launches", "fgd_abi_version",
-    "fgd_measure_fp32_peak",
+    "fgd_measure_fp32_peak", "fgd_set_init_basis", "fgd_init_trajectory",
 )
 
 _lib = None
@@ -80,6 +80,8 @@ def load_library(path: Optional[str] = None):
     lib.fgd_optimize_gd.argtypes = [vp, i32, fp, fp, fp, fp, ip, i32, vp]
     lib.fgd_optimize_host.argtypes = [vp, i32, i32, fp, fp, fp, fp, ip, vp]
     lib.fgd_argmin_per_problem.argtypes = [vp, i32, i32, fp, ip, i32, fp, ip, vp]
+    lib.fgd_set_init_basis.argtypes = [vp, fp, fp, fp]
+    lib.fgd_init_trajectory.argtypes = [vp, i32, fp, fp, fp, vp]
     lib.fgd_launch_geometry.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     lib.fgd_kernel_launches.argtypes = [vp]
     lib.fgd_kernel_launches.restype = C.c_int64
@@ -227,6 +229,17 @@ class Handle:
         self._check(self._lib.fgd_argmin_per_problem(self._h, n_problems, n_restarts, _ptr(fstate), _ptr(istate),
                                                      index_offset, _ptr(best_cost), _ptr(best_index), self._stream()),
                     "fgd_argmin_per_problem")
+
+    # -- device-side initTrajectory ----------------------------------------
+    def set_init_basis(self, u: np.ndarray, w: np.ndarray, jinv: np.ndarray):
+        u, w = np.ascontiguousarray(u, np.float32), np.ascontiguousarray(w, np.float32)
+        jinv = np.ascontiguousarray(jinv, np.float32).reshape(9)
+        assert u.shape == (self.T,) and w.shape == (self.T,)
+        self._check(self._lib.fgd_set_init_basis(self._h, _ptr(u), _ptr(w), _ptr(jinv)), "fgd_set_init_basis")
+
+    def init_trajectory(self, B, start, goal, alpha):
+        self._check(self._lib.fgd_init_trajectory(self._h, B, _ptr(start), _ptr(goal), _ptr(alpha), self._stream()),
+                    "fgd_init_trajectory")
 
     def launch_geometry(self, B: int):
         g, b, s, t = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()

@@ -18,6 +18,7 @@ struct FgdHandle {
     bool k_in_smem;
     int device, num_sms, max_smem_optin;
     float *d_KD = nullptr, *d_KO = nullptr;
+    float *d_init = nullptr;   // [2T + 9]: u = K^-1 1, w = K^-1 c, J^-1 (fgd_set_init_basis)
     float *d_obs[2] = {nullptr, nullptr};
     int obs_active = 0, obs_count = 0;
     unsigned *d_queue = nullptr;
@@ -312,6 +313,7 @@ int fgd_create(const FgdConfig *cfg, FgdHandle **out)
 int fgd_destroy(FgdHandle *h)
 {
     if (!h) return FGD_OK;
+    cudaFree(h->d_init);
     cudaFree(h->d_KD); cudaFree(h->d_KO); cudaFree(h->d_obs[0]); cudaFree(h->d_obs[1]); cudaFree(h->d_queue);
     cudaFree(h->s_alpha); cudaFree(h->s_start); cudaFree(h->s_goal); cudaFree(h->s_fstate); cudaFree(h->s_istate);
     if (h->obs_event) cudaEventDestroy(h->obs_event);
@@ -414,6 +416,32 @@ int fgd_argmin_per_problem(FgdHandle *h, int32_t n_problems, int32_t n_restarts,
     const int block = 256, per = block / 32;
     const int grid = (n_problems + per - 1) / per;
     fgd_argmin_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(n_problems, n_restarts, d_fstate, d_istate, index_offset, d_best_cost, d_best_index);
+    CK(cudaGetLastError());
+    h->launches += 1;
+    return FGD_OK;
+}
+
+int fgd_set_init_basis(FgdHandle *h, const float *h_u, const float *h_w, const float *h_jinv)
+{
+    if (!h || !h_u || !h_w || !h_jinv) return FGD_ERR_INVALID_ARGUMENT;
+    const int T = h->T;
+    std::vector<float> buf((size_t)2 * T + 9);
+    std::memcpy(buf.data(), h_u, (size_t)T * 4);
+    std::memcpy(buf.data() + T, h_w, (size_t)T * 4);
+    std::memcpy(buf.data() + 2 * T, h_jinv, 9 * 4);
+    if (!h->d_init) CK(cudaMalloc(&h->d_init, buf.size() * 4));
+    CK(cudaMemcpy(h->d_init, buf.data(), buf.size() * 4, cudaMemcpyHostToDevice));
+    return FGD_OK;
+}
+
+int fgd_init_trajectory(FgdHandle *h, int32_t B, const float *d_start, const float *d_goal, float *d_alpha, void *stream)
+{
+    if (!h || B < 0 || (B > 0 && (!d_start || !d_goal || !d_alpha)) || !h->d_init) return FGD_ERR_INVALID_ARGUMENT;
+    if (B == 0) return FGD_OK;
+    const long long n = (long long)B * h->T;
+    long long blocks = (n + 255) / 256, cap = (long long)h->num_sms * 8;
+    fgd_init_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(B, h->T, h->d_init, h->d_init + 2 * h->T,
+                                                                                         d_start, d_goal, d_alpha);
     CK(cudaGetLastError());
     h->launches += 1;
     return FGD_OK;

@@ -121,6 +121,25 @@ __device__ __forceinline__ bool gall(bool pred, const Group<LPT> &G)
 
 __device__ __forceinline__ float ss3(float a, float b, float c) { return fmaf(c, c, fmaf(b, b, a * a)); }
 
+// ---------------------------------------------------------------------------
+// Packed FP32 (sm_100 FFMA2 / FMUL2 / FADD2).  A lane's R adjacent time samples
+// are handled as R/2 row pairs: .x = row 2p, .y = row 2p+1.  Every packed
+// instruction is two independent IEEE-754 round-to-nearest operations, so the
+// results are bit-identical to the scalar sequence of the mirror oracle while
+// the instruction count per row halves.  Scalars (constants, obstacle
+// coordinates, operand rows) enter through the .F32 broadcast operand form.
+// ---------------------------------------------------------------------------
+typedef float2 f2;
+__device__ __forceinline__ f2 mk2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ f2 bc2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ f2 neg2(f2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) { return __fadd2_rn(a, neg2(b)); }      // a - b == a + (-b) bit for bit
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ f2 sel2(bool mx, bool my, f2 a, f2 b) { return make_float2(mx ? a.x : b.x, my ? a.y : b.y); }
+__device__ __forceinline__ f2 ss3_2(f2 a, f2 b, f2 c) { return fma2(c, c, fma2(b, b, mul2(a, a))); }
+
 template <bool STRICT>
 __device__ __forceinline__ float rcp(float x)
 {
@@ -133,22 +152,11 @@ __device__ __forceinline__ float rcp(float x)
     }
 }
 
-// sin and cos of one angle: Cody-Waite reduction by pi/2 (3 constants) and the
+// sin and cos of two angles: Cody-Waite reduction by pi/2 (3 constants) and the
 // cephes minimax polynomials on [-pi/4, pi/4]; <= 2 ulp for the angles a 3-joint
 // arm with limits [-1, 2] rad produces.  Same operation sequence as the oracle.
-__device__ __forceinline__ void sincos_cw(float x, float &S, float &C)
+__device__ __forceinline__ void quadrant(float j, float sn, float cs, float &S, float &C)
 {
-    const float j = rintf(x * 6.366197467e-01f);
-    float r = fmaf(j, -1.570796371e+00f, x);
-    r = fmaf(j, 4.371138829e-08f, r);
-    r = fmaf(j, 1.715124510e-15f, r);
-    const float s = r * r;
-    float ps = fmaf(s, -1.9515295891e-4f, 8.3321608736e-3f);
-    ps = fmaf(ps, s, -1.6666654611e-1f);
-    const float sn = fmaf(ps * s, r, r);
-    float pc = fmaf(s, 2.443315711809948e-5f, -1.388731625493765e-3f);
-    pc = fmaf(pc, s, 4.166664568298827e-2f);
-    const float cs = fmaf(pc * s, s, fmaf(-0.5f, s, 1.0f));
     const int n = ((int)j) & 3;
     S = (n & 1) ? cs : sn;
     C = (n & 1) ? sn : cs;
@@ -156,28 +164,49 @@ __device__ __forceinline__ void sincos_cw(float x, float &S, float &C)
     if (n >= 2) S = -S;
 }
 
+__device__ __forceinline__ void sincos_cw2(f2 x, f2 &S, f2 &C)
+{
+    const f2 jj = mul2(x, bc2(6.366197467e-01f));
+    const f2 j = mk2(rintf(jj.x), rintf(jj.y));
+    f2 r = fma2(j, bc2(-1.570796371e+00f), x);
+    r = fma2(j, bc2(4.371138829e-08f), r);
+    r = fma2(j, bc2(1.715124510e-15f), r);
+    const f2 s = mul2(r, r);
+    f2 ps = fma2(s, bc2(-1.9515295891e-4f), bc2(8.3321608736e-3f));
+    ps = fma2(ps, s, bc2(-1.6666654611e-1f));
+    const f2 sn = fma2(mul2(ps, s), r, r);
+    f2 pc = fma2(s, bc2(2.443315711809948e-5f), bc2(-1.388731625493765e-3f));
+    pc = fma2(pc, s, bc2(4.166664568298827e-2f));
+    const f2 cs = fma2(mul2(pc, s), s, fma2(bc2(-0.5f), s, bc2(1.0f)));
+    quadrant(j.x, sn.x, cs.x, S.x, C.x);
+    quadrant(j.y, sn.y, cs.y, S.y, C.y);
+}
+
 // ---------------------------------------------------------------------------
 // RKHS contraction for the trajectory of this lane's group:
 //   y1[r][a] = sum_k K [t_r][k] * x1[k][a]      (trajectory.py:65 / :295)
 //   y2[r][a] = sum_k dK[t_r][k] * x2[k][a]
-// k ascending, one fmaf per term.  KD is the interleaved operand table
+// k ascending, one fma per term.  KD is the interleaved operand table
 //   KD[k][lane][0..R-1] = K[t_r][k],  KD[k][lane][R..2R-1] = dK[t_r][k]
 // (row stride 2*TP floats, TP = LPT*R compile-time), so a lane fetches all its
-// entries of column k with 2R/4 LDS.128 at immediate offsets.  It comes from
-// shared memory (KS) or, for T > 128, from L2 through the read-only path.
+// entries of column k with 2R/4 LDS.128 at immediate offsets and adjacent rows
+// land in aligned register pairs: one FFMA2 per row pair and joint, the operand
+// x[k][a] entering as a broadcast scalar.  The table comes from shared memory
+// (KS) or, for T > 64, from L2 through the read-only path.
 // SAME = true: x1 == x2 (forward evaluation), one operand load per k.
 // ---------------------------------------------------------------------------
 template <int LPT, int R, bool KS, bool SAME>
 __device__ __forceinline__ void contract(const float *__restrict__ kd, int T,
                                          const float4 *__restrict__ x1, const float4 *__restrict__ x2,
-                                         float (&y1)[R][3], float (&y2)[R][3])
+                                         f2 (&y1)[R / 2][3], f2 (&y2)[R / 2][3])
 {
+    constexpr int RP = R / 2;
     constexpr int STRIDE = 2 * LPT * R;       // floats per column k
     constexpr int UNROLL = (R >= 8) ? 2 : ((R == 4) ? 3 : 5);
 #pragma unroll
-    for (int r = 0; r < R; ++r)
+    for (int p = 0; p < RP; ++p)
 #pragma unroll
-        for (int a = 0; a < 3; ++a) { y1[r][a] = 0.0f; y2[r][a] = 0.0f; }
+        for (int a = 0; a < 3; ++a) { y1[p][a] = bc2(0.0f); y2[p][a] = bc2(0.0f); }
 
 #pragma unroll UNROLL
     for (int k = 0; k < T; ++k) {
@@ -193,13 +222,14 @@ __device__ __forceinline__ void contract(const float *__restrict__ kd, int T,
         float4 xb = xa;
         if constexpr (!SAME) xb = x2[k];
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            y1[r][0] = fmaf(kv[r], xa.x, y1[r][0]);
-            y1[r][1] = fmaf(kv[r], xa.y, y1[r][1]);
-            y1[r][2] = fmaf(kv[r], xa.z, y1[r][2]);
-            y2[r][0] = fmaf(kv[R + r], xb.x, y2[r][0]);
-            y2[r][1] = fmaf(kv[R + r], xb.y, y2[r][1]);
-            y2[r][2] = fmaf(kv[R + r], xb.z, y2[r][2]);
+        for (int p = 0; p < RP; ++p) {
+            const f2 kk = mk2(kv[2 * p], kv[2 * p + 1]), dk = mk2(kv[R + 2 * p], kv[R + 2 * p + 1]);
+            y1[p][0] = fma2(kk, bc2(xa.x), y1[p][0]);
+            y1[p][1] = fma2(kk, bc2(xa.y), y1[p][1]);
+            y1[p][2] = fma2(kk, bc2(xa.z), y1[p][2]);
+            y2[p][0] = fma2(dk, bc2(xb.x), y2[p][0]);
+            y2[p][1] = fma2(dk, bc2(xb.y), y2[p][1]);
+            y2[p][2] = fma2(dk, bc2(xb.z), y2[p][2]);
         }
     }
 }
@@ -215,14 +245,15 @@ __device__ __forceinline__ void contract(const float *__restrict__ kd, int T,
 template <int LPT, int R, bool KS>
 __device__ __forceinline__ void contract_back(const float *__restrict__ ko, const float *__restrict__ kd, int T,
                                               const float4 *__restrict__ xa_rows, const float4 *__restrict__ xb_rows,
-                                              const unsigned (&nz)[R], float (&y1)[R][3], float (&y2)[R][3])
+                                              const unsigned (&nz)[R], f2 (&y1)[R / 2][3], f2 (&y2)[R / 2][3])
 {
+    constexpr int RP = R / 2;
     constexpr int SO = LPT * R, SD = 2 * LPT * R;
     constexpr int UNROLL = (R >= 8) ? 2 : ((R == 4) ? 3 : 5);
 #pragma unroll
-    for (int r = 0; r < R; ++r)
+    for (int p = 0; p < RP; ++p)
 #pragma unroll
-        for (int a = 0; a < 3; ++a) { y1[r][a] = 0.0f; y2[r][a] = 0.0f; }
+        for (int a = 0; a < 3; ++a) { y1[p][a] = bc2(0.0f); y2[p][a] = bc2(0.0f); }
 #pragma unroll UNROLL
     for (int k = 0; k < T; ++k) {
         float kv[R];
@@ -242,10 +273,11 @@ __device__ __forceinline__ void contract_back(const float *__restrict__ ko, cons
         }
         const float4 xa = xa_rows[k];
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            y1[r][0] = fmaf(kv[r], xa.x, y1[r][0]);
-            y1[r][1] = fmaf(kv[r], xa.y, y1[r][1]);
-            y1[r][2] = fmaf(kv[r], xa.z, y1[r][2]);
+        for (int p = 0; p < RP; ++p) {
+            const f2 kk = mk2(kv[2 * p], kv[2 * p + 1]);
+            y1[p][0] = fma2(kk, bc2(xa.x), y1[p][0]);
+            y1[p][1] = fma2(kk, bc2(xa.y), y1[p][1]);
+            y1[p][2] = fma2(kk, bc2(xa.z), y1[p][2]);
         }
     }
     unsigned any = 0u;
@@ -259,43 +291,43 @@ __device__ __forceinline__ void contract_back(const float *__restrict__ ko, cons
             if ((nz[r] >> l) & 1u) {
                 const int k = l * R + r;
                 const float4 xb = xb_rows[k];
-                const float *col = kd + (size_t)k * SD + R;
+                const float2 *col = reinterpret_cast<const float2 *>(kd + (size_t)k * SD + R);
 #pragma unroll
-                for (int q = 0; q < R; ++q) {
-                    const float dv = KS ? col[q] : __ldg(col + q);
-                    y2[q][0] = fmaf(dv, xb.x, y2[q][0]);
-                    y2[q][1] = fmaf(dv, xb.y, y2[q][1]);
-                    y2[q][2] = fmaf(dv, xb.z, y2[q][2]);
+                for (int p = 0; p < RP; ++p) {
+                    const f2 dv = KS ? col[p] : __ldg(col + p);
+                    y2[p][0] = fma2(dv, bc2(xb.x), y2[p][0]);
+                    y2[p][1] = fma2(dv, bc2(xb.y), y2[p][1]);
+                    y2[p][2] = fma2(dv, bc2(xb.z), y2[p][2]);
                 }
             }
         }
     }
 }
 
-// Per-lane rows kept between the cost phase and the gradient phase.  LEAN variants (R >= 4)
+// Per-lane row pairs kept between the cost phase and the gradient phase.  LEAN variants (R >= 4)
 // keep only the obstacle gradient and recompute q, v and the sines/cosines in the gradient
 // phase from the contraction rows (same arithmetic, same bits) to stay out of the spill zone.
 template <int R, bool LEAN>
 struct Rows {
-    float q[LEAN ? 1 : R][3], v[LEAN ? 1 : R][3], sn[LEAN ? 1 : R][3], cs[LEAN ? 1 : R][3];
-    float gx[R], gy[R];
+    f2 q[LEAN ? 1 : R / 2][3], v[LEAN ? 1 : R / 2][3], sn[LEAN ? 1 : R / 2][3], cs[LEAN ? 1 : R / 2][3];
+    f2 gx[R / 2], gy[R / 2];
     int amax;
 };
 
-// q, v rows from the raw contraction rows ((M @ alpha) @ J, trajectory.py:65) and the
+// q, v of a row pair from the raw contraction rows ((M @ alpha) @ J, trajectory.py:65) and the
 // sines / cosines of the cumulative joint angles (robot.py:32).
-__device__ __forceinline__ void row_kinematics(const DevParams &p, const float (&yq)[3], const float (&yv)[3],
-                                               float (&q)[3], float (&v)[3], float (&sn)[3], float (&cs)[3])
+__device__ __forceinline__ void row_kinematics(const DevParams &p, const f2 (&yq)[3], const f2 (&yv)[3],
+                                               f2 (&q)[3], f2 (&v)[3], f2 (&sn)[3], f2 (&cs)[3])
 {
 #pragma unroll
     for (int b = 0; b < 3; ++b) {
-        q[b] = fmaf(yq[2], p.J[6 + b], fmaf(yq[1], p.J[3 + b], yq[0] * p.J[b]));
-        v[b] = fmaf(yv[2], p.J[6 + b], fmaf(yv[1], p.J[3 + b], yv[0] * p.J[b]));
+        q[b] = fma2(yq[2], bc2(p.J[6 + b]), fma2(yq[1], bc2(p.J[3 + b]), mul2(yq[0], bc2(p.J[b]))));
+        v[b] = fma2(yv[2], bc2(p.J[6 + b]), fma2(yv[1], bc2(p.J[3 + b]), mul2(yv[0], bc2(p.J[b]))));
     }
-    const float c1 = q[0], c2 = c1 + q[1], c3 = c2 + q[2];
-    sincos_cw(c1, sn[0], cs[0]);
-    sincos_cw(c2, sn[1], cs[1]);
-    sincos_cw(c3, sn[2], cs[2]);
+    const f2 c1 = q[0], c2 = add2(c1, q[1]), c3 = add2(c2, q[2]);
+    sincos_cw2(c1, sn[0], cs[0]);
+    sincos_cw2(c2, sn[1], cs[1]);
+    sincos_cw2(c3, sn[2], cs[2]);
 }
 
 // ---------------------------------------------------------------------------
@@ -309,92 +341,109 @@ __device__ __forceinline__ void row_kinematics(const DevParams &p, const float (
 // ---------------------------------------------------------------------------
 template <int LPT, int R, bool STRICT, bool LEAN>
 __device__ __forceinline__ void cost_phase(const DevParams &p, const float2 *__restrict__ sObs, const Group<LPT> &G,
-                                           const float (&yq)[R][3], const float (&yv)[R][3],
+                                           const f2 (&yq)[R / 2][3], const f2 (&yv)[R / 2][3],
                                            const float *start, const float *goal, float lam_sg, float lam_jl,
                                            Rows<R, LEAN> &Rw, float &loss, float &toc, int &ful)
 {
+    constexpr int RP = R / 2;
     const int T = p.T;
     const int t0 = G.gl * R;
     const int lT = (T - 1) / R, rT = (T - 1) % R;
     float part_c = 0.0f, part_p = 0.0f, part_v = 0.0f, lmax = 0.0f;
     bool lim_ok = true;
-    float x[R], y[R], sr[R], sx[R], sy[R];
+    f2 x[RP], y[RP], sr[RP], sx[RP], sy[RP];
     float ssp0 = 0.0f, ssv0 = 0.0f, sspT = 0.0f, ssvT = 0.0f;      // meaningful in the lanes owning rows 0 / T-1
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const bool valid = (t0 + r) < T;
-        float q[3], v[3], sn[3], cs[3];
-        row_kinematics(p, yq[r], yv[r], q, v, sn, cs);
+    for (int pr = 0; pr < RP; ++pr) {
+        const bool valid0 = (t0 + 2 * pr) < T, valid1 = (t0 + 2 * pr + 1) < T;
+        f2 q[3], v[3], sn[3], cs[3];
+        row_kinematics(p, yq[pr], yv[pr], q, v, sn, cs);
         if constexpr (!LEAN) {
 #pragma unroll
-            for (int b = 0; b < 3; ++b) { Rw.q[r][b] = q[b]; Rw.v[r][b] = v[b]; Rw.sn[r][b] = sn[b]; Rw.cs[r][b] = cs[b]; }
+            for (int b = 0; b < 3; ++b) { Rw.q[pr][b] = q[b]; Rw.v[pr][b] = v[b]; Rw.sn[pr][b] = sn[b]; Rw.cs[pr][b] = cs[b]; }
         }
-        x[r] = fmaf(p.link[2], cs[2], fmaf(p.link[1], cs[1], p.link[0] * cs[0]));     // robot.py:33
-        y[r] = fmaf(p.link[2], sn[2], fmaf(p.link[1], sn[1], p.link[0] * sn[0]));     // robot.py:34
-        sr[r] = 0.0f; sx[r] = 0.0f; sy[r] = 0.0f;
-        // joint-limit penalties and limit predicates of this row   trajectory.py:215-255, robot.py:104-113
-        float e3[3], f3[3];
+        x[pr] = fma2(bc2(p.link[2]), cs[2], fma2(bc2(p.link[1]), cs[1], mul2(bc2(p.link[0]), cs[0])));     // robot.py:33
+        y[pr] = fma2(bc2(p.link[2]), sn[2], fma2(bc2(p.link[1]), sn[1], mul2(bc2(p.link[0]), sn[0])));     // robot.py:34
+        sr[pr] = bc2(0.0f); sx[pr] = bc2(0.0f); sy[pr] = bc2(0.0f);
+        // joint-limit penalties and limit predicates of these rows   trajectory.py:215-255, robot.py:104-113
+        f2 e3[3], f3[3];
+        bool ok0 = true, ok1 = true;
 #pragma unroll
         for (int b = 0; b < 3; ++b) {
-            const float qb = q[b], vb = v[b];
-            const float u = (qb - p.mean_q) * p.inv_std;
-            const bool m = p.cvdl ? (qb > p.q_hi || qb < p.q_lo) : true;
-            e3[b] = m ? 0.5f * (u * u) : 0.0f;
-            const float w = vb * p.inv_vmax;
-            const bool mv = p.cvdl ? (fabsf(vb) > p.v_hi) : true;
-            f3[b] = mv ? 0.5f * (w * w) : 0.0f;
-            lim_ok = lim_ok & (!valid | ((qb <= p.qmax) & (qb >= p.qmin) & (fabsf(vb) <= p.vmax)));
+            const f2 qb = q[b], vb = v[b];
+            const f2 u = mul2(add2(qb, bc2(-p.mean_q)), bc2(p.inv_std));
+            const f2 hu = mul2(bc2(0.5f), mul2(u, u));
+            const bool m0 = p.cvdl ? (qb.x > p.q_hi || qb.x < p.q_lo) : true;
+            const bool m1 = p.cvdl ? (qb.y > p.q_hi || qb.y < p.q_lo) : true;
+            e3[b] = sel2(m0, m1, hu, bc2(0.0f));
+            const f2 w = mul2(vb, bc2(p.inv_vmax));
+            const f2 hw = mul2(bc2(0.5f), mul2(w, w));
+            const bool n0 = p.cvdl ? (fabsf(vb.x) > p.v_hi) : true;
+            const bool n1 = p.cvdl ? (fabsf(vb.y) > p.v_hi) : true;
+            f3[b] = sel2(n0, n1, hw, bc2(0.0f));
+            ok0 = ok0 & ((qb.x <= p.qmax) & (qb.x >= p.qmin) & (fabsf(vb.x) <= p.vmax));
+            ok1 = ok1 & ((qb.y <= p.qmax) & (qb.y >= p.qmin) & (fabsf(vb.y) <= p.vmax));
         }
-        if (valid) {
-            part_p = part_p + ((e3[0] + e3[1]) + e3[2]);
-            part_v = part_v + ((f3[0] + f3[1]) + f3[2]);
-        }
+        lim_ok = lim_ok & (!valid0 | ok0) & (!valid1 | ok1);
+        const f2 es = add2(add2(e3[0], e3[1]), e3[2]), fs = add2(add2(f3[0], f3[1]), f3[2]);
+        if (valid0) { part_p = part_p + es.x; part_v = part_v + fs.x; }
+        if (valid1) { part_p = part_p + es.y; part_v = part_v + fs.y; }
         // start / goal rows   trajectory.py:183-204
-        if (r == 0) {
-            ssp0 = ss3(q[0] - start[0], q[1] - start[1], q[2] - start[2]);
-            ssv0 = ss3(v[0], v[1], v[2]);
+        if (pr == 0) {
+            ssp0 = ss3(q[0].x - start[0], q[1].x - start[1], q[2].x - start[2]);
+            ssv0 = ss3(v[0].x, v[1].x, v[2].x);
         }
-        if (r == rT) {
-            sspT = ss3(q[0] - goal[0], q[1] - goal[1], q[2] - goal[2]);
-            ssvT = ss3(v[0], v[1], v[2]);
+        if (2 * pr == rT) {
+            sspT = ss3(q[0].x - goal[0], q[1].x - goal[1], q[2].x - goal[2]);
+            ssvT = ss3(v[0].x, v[1].x, v[2].x);
+        }
+        if (2 * pr + 1 == rT) {
+            sspT = ss3(q[0].y - goal[0], q[1].y - goal[1], q[2].y - goal[2]);
+            ssvT = ss3(v[0].y, v[1].y, v[2].y);
         }
     }
     // obstacle potential: all R samples of this lane against every obstacle
     const int n_obs = p.n_obs;
-    constexpr int OBS_UNROLL = (R >= 8) ? 1 : 2;      // R independent chains per obstacle already
+    constexpr int OBS_UNROLL = (R >= 8) ? 1 : ((R == 4) ? 2 : 4);      // R/2 independent packed chains per obstacle already
     float2 ob_next = sObs[0];                       // software pipelining: the next obstacle is fetched one trip ahead
 #pragma unroll OBS_UNROLL
     for (int o = 0; o < n_obs; ++o) {
         const float2 ob = ob_next;
         ob_next = sObs[o + 1];                      // the buffer is padded by one pair (make_layout)
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const float dx = x[r] - ob.x, dy = y[r] - ob.y;
-            const float n = fmaf(dy, dy, dx * dx);
-            const float den = fmaf(0.5f, n, 0.5f);
-            const float rr = rcp<STRICT>(den);
-            sr[r] = sr[r] + rr;
-            const float r2 = rr * rr;
-            sx[r] = fmaf(r2, dx, sx[r]);
-            sy[r] = fmaf(r2, dy, sy[r]);
+        for (int pr = 0; pr < RP; ++pr) {
+            const f2 dx = add2(x[pr], bc2(-ob.x)), dy = add2(y[pr], bc2(-ob.y));
+            const f2 n = fma2(dy, dy, mul2(dx, dx));
+            const f2 den = fma2(bc2(0.5f), n, bc2(0.5f));
+            const f2 rr = mk2(rcp<STRICT>(den.x), rcp<STRICT>(den.y));
+            sr[pr] = add2(sr[pr], rr);
+            const f2 r2 = mul2(rr, rr);
+            sx[pr] = fma2(r2, dx, sx[pr]);
+            sy[pr] = fma2(r2, dy, sy[pr]);
         }
     }
-    float cost[R];
+    f2 cost[RP];
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const float c = 0.8f * sr[r];
-        cost[r] = c; Rw.gx[r] = -0.8f * sx[r]; Rw.gy[r] = -0.8f * sy[r];
-        if ((t0 + r) < T) {
-            part_c = part_c + c;
-            lmax = fmaxf(lmax, c);          // c >= 0
+    for (int pr = 0; pr < RP; ++pr) {
+        const f2 c = mul2(bc2(0.8f), sr[pr]);
+        cost[pr] = c; Rw.gx[pr] = mul2(bc2(-0.8f), sx[pr]); Rw.gy[pr] = mul2(bc2(-0.8f), sy[pr]);
+        if ((t0 + 2 * pr) < T) {
+            part_c = part_c + c.x;
+            lmax = fmaxf(lmax, c.x);          // c >= 0
+        }
+        if ((t0 + 2 * pr + 1) < T) {
+            part_c = part_c + c.y;
+            lmax = fmaxf(lmax, c.y);
         }
     }
     // max / first argmax / mean over t
     const float maxc = gmax<LPT>(lmax);
     int cand = 0x7fffffff;
 #pragma unroll
-    for (int r = R - 1; r >= 0; --r)
-        if ((t0 + r) < T && cost[r] == maxc) cand = t0 + r;
+    for (int pr = RP - 1; pr >= 0; --pr) {
+        if ((t0 + 2 * pr + 1) < T && cost[pr].y == maxc) cand = t0 + 2 * pr + 1;
+        if ((t0 + 2 * pr) < T && cost[pr].x == maxc) cand = t0 + 2 * pr;
+    }
     Rw.amax = gmin_int<LPT>(cand);
     const float avg = gsum<LPT>(part_c) / p.fT;
     toc = fmaf(p.lam_max, maxc, p.oml * avg);
@@ -420,64 +469,78 @@ __device__ __forceinline__ void cost_phase(const DevParams &p, const float2 *__r
 // ---------------------------------------------------------------------------
 template <int LPT, int R, bool LEAN>
 __device__ __forceinline__ void grad_phase(const DevParams &p, const Group<LPT> &G, const Rows<R, LEAN> &Rw,
-                                           const float (&yq)[R][3], const float (&yv)[R][3], const float *start, const float *goal,
+                                           const f2 (&yq)[R / 2][3], const f2 (&yv)[R / 2][3], const float *start, const float *goal,
                                            float lam_sg, float lam_jl, float4 *XA, float4 *XB, bool commit, unsigned (&nz)[R])
 {
+    constexpr int RP = R / 2;
     const int T = p.T;
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const int t = G.gl * R + r;
-        float q[3], v[3], sn[3], cs[3];
+    for (int pr = 0; pr < RP; ++pr) {
+        const int ta = G.gl * R + 2 * pr, tb = ta + 1;
+        f2 q[3], v[3], sn[3], cs[3];
         if constexpr (LEAN) {
-            row_kinematics(p, yq[r], yv[r], q, v, sn, cs);
+            row_kinematics(p, yq[pr], yv[pr], q, v, sn, cs);
         } else {
 #pragma unroll
-            for (int b = 0; b < 3; ++b) { q[b] = Rw.q[r][b]; v[b] = Rw.v[r][b]; sn[b] = Rw.sn[r][b]; cs[b] = Rw.cs[r][b]; }
+            for (int b = 0; b < 3; ++b) { q[b] = Rw.q[pr][b]; v[b] = Rw.v[pr][b]; sn[b] = Rw.sn[pr][b]; cs[b] = Rw.cs[pr][b]; }
         }
-        const float wt = (t == Rw.amax) ? (p.lam_max + p.w_avg) : p.w_avg;
-        const float cgx = wt * Rw.gx[r], cgy = wt * Rw.gy[r];
-        float xs[3], ys[3];
+        const float w_hi = p.lam_max + p.w_avg;
+        const f2 wt = mk2((ta == Rw.amax) ? w_hi : p.w_avg, (tb == Rw.amax) ? w_hi : p.w_avg);
+        const f2 cgx = mul2(wt, Rw.gx[pr]), cgy = mul2(wt, Rw.gy[pr]);
+        f2 xs[3], ys[3];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) { xs[k] = -(p.link[k] * sn[k]); ys[k] = p.link[k] * cs[k]; }
-        const float Sx = (xs[0] + xs[1]) + xs[2], Sy = (ys[0] + ys[1]) + ys[2];
-        const float Cx[3] = {xs[0], xs[0] + xs[1], (xs[0] + xs[1]) + xs[2]};
-        const float Cy[3] = {ys[0], ys[0] + ys[1], (ys[0] + ys[1]) + ys[2]};
-        float gq[3], gv[3];
+        for (int k = 0; k < 3; ++k) { xs[k] = neg2(mul2(bc2(p.link[k]), sn[k])); ys[k] = mul2(bc2(p.link[k]), cs[k]); }
+        const f2 Sx = add2(add2(xs[0], xs[1]), xs[2]), Sy = add2(add2(ys[0], ys[1]), ys[2]);
+        const f2 Cx[3] = {xs[0], add2(xs[0], xs[1]), add2(add2(xs[0], xs[1]), xs[2])};
+        const f2 Cy[3] = {ys[0], add2(ys[0], ys[1]), add2(add2(ys[0], ys[1]), ys[2])};
+        f2 gq[3], gv[3];
+        const bool a0 = (ta == 0), aT = (ta == T - 1), b0 = false, bT = (tb == T - 1);     // tb >= 1
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            const float Jx = (xs[k] + Sx) - Cx[k];
-            const float Jy = (ys[k] + Sy) - Cy[k];
-            const float tg = fmaf(cgy, Jy, cgx * Jx);
-            const float qk = q[k], vk = v[k];
-            const float sgp = (t == 0) ? (qk - start[k]) : ((t == T - 1) ? (qk - goal[k]) : 0.0f);
-            const float sgv = (t == 0 || t == T - 1) ? vk : 0.0f;
-            const bool m = p.cvdl ? (qk > p.q_hi || qk < p.q_lo) : true;
-            const float jpg = m ? ((qk - p.mean_q) * p.inv_std2) * p.inv_T : 0.0f;
-            const bool mv = p.cvdl ? (fabsf(vk) > p.v_hi) : true;
-            const float jvg = mv ? (vk * p.inv_vmax2) * p.inv_T : 0.0f;
-            gq[k] = fmaf(lam_jl, jpg, fmaf(lam_sg, sgp, tg));
-            gv[k] = fmaf(lam_jl, jvg, lam_sg * sgv);
+            const f2 Jx = sub2(add2(xs[k], Sx), Cx[k]);
+            const f2 Jy = sub2(add2(ys[k], Sy), Cy[k]);
+            const f2 tg = fma2(cgy, Jy, mul2(cgx, Jx));
+            const f2 qk = q[k], vk = v[k];
+            f2 sgp, sgv;
+            sgp.x = a0 ? (qk.x - start[k]) : (aT ? (qk.x - goal[k]) : 0.0f);
+            sgp.y = b0 ? (qk.y - start[k]) : (bT ? (qk.y - goal[k]) : 0.0f);
+            sgv.x = (a0 || aT) ? vk.x : 0.0f;
+            sgv.y = (b0 || bT) ? vk.y : 0.0f;
+            const bool m0 = p.cvdl ? (qk.x > p.q_hi || qk.x < p.q_lo) : true;
+            const bool m1 = p.cvdl ? (qk.y > p.q_hi || qk.y < p.q_lo) : true;
+            const f2 jpg = sel2(m0, m1, mul2(mul2(add2(qk, bc2(-p.mean_q)), bc2(p.inv_std2)), bc2(p.inv_T)), bc2(0.0f));
+            const bool n0 = p.cvdl ? (fabsf(vk.x) > p.v_hi) : true;
+            const bool n1 = p.cvdl ? (fabsf(vk.y) > p.v_hi) : true;
+            const f2 jvg = sel2(n0, n1, mul2(mul2(vk, bc2(p.inv_vmax2)), bc2(p.inv_T)), bc2(0.0f));
+            gq[k] = fma2(bc2(lam_jl), jpg, fma2(bc2(lam_sg), sgp, tg));
+            gv[k] = fma2(bc2(lam_jl), jvg, mul2(bc2(lam_sg), sgv));
         }
-        const bool write = commit && t < T;
-        if (write) {
-            XA[t] = make_float4(gq[0], gq[1], gq[2], 0.0f);
-            XB[t] = make_float4(-gv[0], -gv[1], -gv[2], 0.0f);
+        const bool wa = commit && ta < T, wb = commit && tb < T;
+        if (wa) {
+            XA[ta] = make_float4(gq[0].x, gq[1].x, gq[2].x, 0.0f);
+            XB[ta] = make_float4(-gv[0].x, -gv[1].x, -gv[2].x, 0.0f);
         }
-        const unsigned m = __ballot_sync(FULL, write && (gv[0] != 0.0f || gv[1] != 0.0f || gv[2] != 0.0f));
-        if (commit) nz[r] = m;
+        if (wb) {
+            XA[tb] = make_float4(gq[0].y, gq[1].y, gq[2].y, 0.0f);
+            XB[tb] = make_float4(-gv[0].y, -gv[1].y, -gv[2].y, 0.0f);
+        }
+        const unsigned ma = __ballot_sync(FULL, wa && (gv[0].x != 0.0f || gv[1].x != 0.0f || gv[2].x != 0.0f));
+        const unsigned mb = __ballot_sync(FULL, wb && (gv[0].y != 0.0f || gv[1].y != 0.0f || gv[2].y != 0.0f));
+        if (commit) { nz[2 * pr] = ma; nz[2 * pr + 1] = mb; }
     }
 }
 
 // alpha-gradient rows from the backward contraction: (K^T G_q + dK^T G_v) J^T
 template <int R>
-__device__ __forceinline__ void backward_rows(const DevParams &p, const float (&y1)[R][3], const float (&y2)[R][3],
-                                              float (&g)[R][3])
+__device__ __forceinline__ void backward_rows(const DevParams &p, const f2 (&y1)[R / 2][3], const f2 (&y2)[R / 2][3],
+                                              f2 (&g)[R / 2][3])
 {
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const float r0 = y1[r][0] + y2[r][0], r1 = y1[r][1] + y2[r][1], r2 = y1[r][2] + y2[r][2];
+    for (int pr = 0; pr < R / 2; ++pr) {
+        const f2 r0 = add2(y1[pr][0], y2[pr][0]), r1 = add2(y1[pr][1], y2[pr][1]), r2 = add2(y1[pr][2], y2[pr][2]);
 #pragma unroll
-        for (int b = 0; b < 3; ++b) g[r][b] = fmaf(r2, p.J[b * 3 + 2], fmaf(r1, p.J[b * 3 + 1], r0 * p.J[b * 3]));
+        for (int b = 0; b < 3; ++b)
+            g[pr][b] = fma2(r2, bc2(p.J[b * 3 + 2]), fma2(r1, bc2(p.J[b * 3 + 1]), mul2(r0, bc2(p.J[b * 3]))));
     }
 }
 

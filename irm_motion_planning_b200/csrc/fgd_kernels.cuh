@@ -44,54 +44,63 @@ __host__ __device__ inline SmemLayout make_layout(int T, int TP, int n_obs, bool
 
 // lane-major row store: slot (r, lane) -> buf[r * 32 + lane]   (conflict-free for a warp)
 template <int R>
-__device__ __forceinline__ void ld_rows(const float4 *buf, int lane, float (&x)[R][3])
+__device__ __forceinline__ void ld_rows(const float4 *buf, int lane, f2 (&x)[R / 2][3])
 {
 #pragma unroll
-    for (int r = 0; r < R; ++r) { const float4 v = buf[r * 32 + lane]; x[r][0] = v.x; x[r][1] = v.y; x[r][2] = v.z; }
+    for (int pr = 0; pr < R / 2; ++pr) {
+        const float4 u = buf[(2 * pr) * 32 + lane], v = buf[(2 * pr + 1) * 32 + lane];
+        x[pr][0] = mk2(u.x, v.x); x[pr][1] = mk2(u.y, v.y); x[pr][2] = mk2(u.z, v.z);
+    }
 }
 template <int R>
-__device__ __forceinline__ void st_rows(float4 *buf, int lane, const float (&x)[R][3])
+__device__ __forceinline__ void st_rows(float4 *buf, int lane, const f2 (&x)[R / 2][3])
 {
 #pragma unroll
-    for (int r = 0; r < R; ++r) buf[r * 32 + lane] = make_float4(x[r][0], x[r][1], x[r][2], 0.0f);
+    for (int pr = 0; pr < R / 2; ++pr) {
+        buf[(2 * pr) * 32 + lane] = make_float4(x[pr][0].x, x[pr][1].x, x[pr][2].x, 0.0f);
+        buf[(2 * pr + 1) * 32 + lane] = make_float4(x[pr][0].y, x[pr][1].y, x[pr][2].y, 0.0f);
+    }
 }
 
 __device__ __forceinline__ void hash_step(Slot &st, unsigned code) { st.hash = st.hash * 1000003u + code; }
 
 // candidate  (1 - lam_reg*lr) * alpha - lr * dir      optimizer_BLS.py:139, optimizer_GD.py:185
 template <int LPT, int R>
-__device__ __forceinline__ void write_candidate(const DevParams &p, const Group<LPT> &G, float lr, const float (&a)[R][3],
-                                                const float (&d)[R][3], float4 *XA)
+__device__ __forceinline__ void write_candidate(const DevParams &p, const Group<LPT> &G, float lr, const f2 (&a)[R / 2][3],
+                                                const f2 (&d)[R / 2][3], float4 *XA)
 {
     const float c1 = 1.0f - p.lam_reg * lr;
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const int t = G.gl * R + r;
-        if (t < p.T)
-            XA[t] = make_float4(fmaf(c1, a[r][0], -(lr * d[r][0])), fmaf(c1, a[r][1], -(lr * d[r][1])),
-                                fmaf(c1, a[r][2], -(lr * d[r][2])), 0.0f);
+    for (int pr = 0; pr < R / 2; ++pr) {
+        const int t = G.gl * R + 2 * pr;
+        f2 c[3];
+#pragma unroll
+        for (int b = 0; b < 3; ++b) c[b] = fma2(bc2(c1), a[pr][b], neg2(mul2(bc2(lr), d[pr][b])));
+        if (t < p.T) XA[t] = make_float4(c[0].x, c[1].x, c[2].x, 0.0f);
+        if (t + 1 < p.T) XA[t + 1] = make_float4(c[0].y, c[1].y, c[2].y, 0.0f);
     }
 }
 
 template <int R>
-__device__ __forceinline__ void accept_candidate(const DevParams &p, float lr, float (&a)[R][3], const float (&d)[R][3])
+__device__ __forceinline__ void accept_candidate(const DevParams &p, float lr, f2 (&a)[R / 2][3], const f2 (&d)[R / 2][3])
 {
     const float c1 = 1.0f - p.lam_reg * lr;
 #pragma unroll
-    for (int r = 0; r < R; ++r)
+    for (int pr = 0; pr < R / 2; ++pr)
 #pragma unroll
-        for (int b = 0; b < 3; ++b) a[r][b] = fmaf(c1, a[r][b], -(lr * d[r][b]));
+        for (int b = 0; b < 3; ++b) a[pr][b] = fma2(bc2(c1), a[pr][b], neg2(mul2(bc2(lr), d[pr][b])));
 }
 
 template <int LPT, int R>
-__device__ __forceinline__ void save_slot(const DevParams &p, const Group<LPT> &G, const Slot &st, int status, const float (&a)[R][3])
+__device__ __forceinline__ void save_slot(const DevParams &p, const Group<LPT> &G, const Slot &st, int status, const f2 (&a)[R / 2][3])
 {
     const int b = st.traj;
     float *ap = p.alpha + (size_t)b * p.T * 3;
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const int t = G.gl * R + r;
-        if (t < p.T) { ap[t * 3] = a[r][0]; ap[t * 3 + 1] = a[r][1]; ap[t * 3 + 2] = a[r][2]; }
+    for (int pr = 0; pr < R / 2; ++pr) {
+        const int t = G.gl * R + 2 * pr;
+        if (t < p.T) { ap[t * 3] = a[pr][0].x; ap[t * 3 + 1] = a[pr][1].x; ap[t * 3 + 2] = a[pr][2].x; }
+        if (t + 1 < p.T) { ap[t * 3 + 3] = a[pr][0].y; ap[t * 3 + 4] = a[pr][1].y; ap[t * 3 + 5] = a[pr][2].y; }
     }
     if (G.gl == 0) {
         float *fs = p.fstate + (size_t)b * FGD_FSTATE;
@@ -107,13 +116,14 @@ __device__ __forceinline__ void save_slot(const DevParams &p, const Group<LPT> &
 // Start (or restart after a lambda increase / a resumed launch) with the loss and
 // gradient operands at the current alpha: optimizer_BLS.py:163, optimizer_GD.py:210.
 template <int LPT, int R>
-__device__ __forceinline__ void begin_outer_eval(const DevParams &p, const Group<LPT> &G, Slot &st, int &kind, const float (&a)[R][3], float4 *XA)
+__device__ __forceinline__ void begin_outer_eval(const DevParams &p, const Group<LPT> &G, Slot &st, int &kind, const f2 (&a)[R / 2][3], float4 *XA)
 {
     if (p.mode == 1) st.lr = p.gd_lr[st.outer];
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const int t = G.gl * R + r;
-        if (t < p.T) XA[t] = make_float4(a[r][0], a[r][1], a[r][2], 0.0f);
+    for (int pr = 0; pr < R / 2; ++pr) {
+        const int t = G.gl * R + 2 * pr;
+        if (t < p.T) XA[t] = make_float4(a[pr][0].x, a[pr][1].x, a[pr][2].x, 0.0f);
+        if (t + 1 < p.T) XA[t + 1] = make_float4(a[pr][0].y, a[pr][1].y, a[pr][2].y, 0.0f);
     }
     kind = K_EVAL0;
 }
@@ -121,7 +131,7 @@ __device__ __forceinline__ void begin_outer_eval(const DevParams &p, const Group
 // Pull the next unfinished trajectory from the batch queue into every group that asks for one.
 // Executed by the whole (converged) warp; `need` is group-uniform.
 template <int LPT, int R>
-__device__ __forceinline__ void fetch_slot(const DevParams &p, const Group<LPT> &G, bool need, Slot &st, int &kind, float (&a)[R][3])
+__device__ __forceinline__ void fetch_slot(const DevParams &p, const Group<LPT> &G, bool need, Slot &st, int &kind, f2 (&a)[R / 2][3])
 {
     for (;;) {
         __syncwarp();
@@ -156,10 +166,11 @@ __device__ __forceinline__ void fetch_slot(const DevParams &p, const Group<LPT> 
                     for (int b = 0; b < 3; ++b) { st.start[b] = p.start[(size_t)idx * 3 + b]; st.goal[b] = p.goal[(size_t)idx * 3 + b]; }
                     const float *ap = p.alpha + (size_t)idx * p.T * 3;
 #pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        const int t = G.gl * R + r;
-                        const bool ok = t < p.T;
-                        a[r][0] = ok ? ap[t * 3] : 0.0f; a[r][1] = ok ? ap[t * 3 + 1] : 0.0f; a[r][2] = ok ? ap[t * 3 + 2] : 0.0f;
+                    for (int pr = 0; pr < R / 2; ++pr) {
+                        const int t = G.gl * R + 2 * pr;
+                        const bool ok = t < p.T, ok1 = t + 1 < p.T;
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) a[pr][c] = mk2(ok ? ap[t * 3 + c] : 0.0f, ok1 ? ap[t * 3 + 3 + c] : 0.0f);
                     }
                     kind = K_EVAL0;
                     need = false;
@@ -227,15 +238,16 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
     unsigned nz[R];            // non-zero rows of the velocity gradient operand (see contract_back)
 #pragma unroll
     for (int r = 0; r < R; ++r) nz[r] = 0u;
-    float a[R][3];     // alpha rows of this lane
-    float d[R][3];     // step direction rows (normalised gradient for BLS, gradient for GD)
+    constexpr int RP = R / 2;
+    f2 a[RP][3];       // alpha rows of this lane, as row pairs (.x = row 2p, .y = row 2p+1)
+    f2 d[RP][3];       // step direction rows (normalised gradient for BLS, gradient for GD)
 #pragma unroll
-    for (int r = 0; r < R; ++r)
+    for (int pr = 0; pr < RP; ++pr)
 #pragma unroll
-        for (int b = 0; b < 3; ++b) { a[r][b] = 0.0f; d[r][b] = 0.0f; }
+        for (int b = 0; b < 3; ++b) { a[pr][b] = bc2(0.0f); d[pr][b] = bc2(0.0f); }
     bool boot = true;          // first trip: nothing to contract yet, just fill the slots through the common tail
     for (;;) {
-        float y1[R][3], y2[R][3];
+        f2 y1[RP][3], y2[RP][3];
         if (!boot) {
             if (!__any_sync(FULL, kind != K_IDLE)) break;
             __syncwarp();
@@ -254,29 +266,34 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
         __syncwarp();
         if (__any_sync(FULL, is_back)) {
             // ---- alpha-gradient, normalisation, first candidate ------------------------------
-            float g[R][3];
+            f2 g[RP][3];
             backward_rows<R>(p, y1, y2, g);
             float alpha_norm = 0.0f, scale = 1.0f;
             if (p.mode == 0) {
                 float part = 0.0f;
 #pragma unroll
-                for (int r = 0; r < R; ++r)
-                    if (G.gl * R + r < T) part = part + ss3(g[r][0], g[r][1], g[r][2]);
+                for (int pr = 0; pr < RP; ++pr) {
+                    const f2 ss = ss3_2(g[pr][0], g[pr][1], g[pr][2]);
+                    if (G.gl * R + 2 * pr < T) part = part + ss.x;
+                    if (G.gl * R + 2 * pr + 1 < T) part = part + ss.y;
+                }
                 scale = 1.0f / sqrtf(gsum<LPT>(part));                                 // optimizer_BLS.py:165
                 float pb = 0.0f;
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    const float n0 = g[r][0] * scale, n1 = g[r][1] * scale, n2 = g[r][2] * scale;
-                    if (G.gl * R + r < T) pb = pb + ((g[r][0] + g[r][1]) + g[r][2]) * ((n0 + n1) + n2);
-                    g[r][0] = n0; g[r][1] = n1; g[r][2] = n2;
+                for (int pr = 0; pr < RP; ++pr) {
+                    const f2 n0 = mul2(g[pr][0], bc2(scale)), n1 = mul2(g[pr][1], bc2(scale)), n2 = mul2(g[pr][2], bc2(scale));
+                    const f2 pp = mul2(add2(add2(g[pr][0], g[pr][1]), g[pr][2]), add2(add2(n0, n1), n2));
+                    if (G.gl * R + 2 * pr < T) pb = pb + pp.x;
+                    if (G.gl * R + 2 * pr + 1 < T) pb = pb + pp.y;
+                    g[pr][0] = n0; g[pr][1] = n1; g[pr][2] = n2;
                 }
                 alpha_norm = gsum<LPT>(pb);                                            // optimizer_BLS.py:166
             }
             if (is_back) {
 #pragma unroll
-                for (int r = 0; r < R; ++r)
+                for (int pr = 0; pr < RP; ++pr)
 #pragma unroll
-                    for (int b = 0; b < 3; ++b) d[r][b] = g[r][b];
+                    for (int b = 0; b < 3; ++b) d[pr][b] = g[pr][b];
                 if constexpr (LEAN) st_rows<R>(SD, G.lane, d);
                 st.alpha_norm = alpha_norm; st.j = 0;
                 want_cand = true;
@@ -436,7 +453,7 @@ __global__ void __launch_bounds__(NW * 32) fgd_eval_kernel(const __grid_constant
 #pragma unroll
             for (int k = 0; k < 3; ++k) { start[k] = p.start[(size_t)b * 3 + k]; goal[k] = p.goal[(size_t)b * 3 + k]; }
         }
-        float y1[R][3], y2[R][3];
+        f2 y1[R / 2][3], y2[R / 2][3];
         MARK(3);
         __syncwarp();
         contract<LPT, R, KS, true>(kd, T, XA, XA, y1, y2);
@@ -455,15 +472,19 @@ __global__ void __launch_bounds__(NW * 32) fgd_eval_kernel(const __grid_constant
                 if (e.fulfilled) e.fulfilled[b] = ful;
             }
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const int t = G.gl * R + r;
+            for (int pr = 0; pr < R / 2; ++pr) {
+                const int t = G.gl * R + 2 * pr;
                 if (live && t < T && (e.q || e.v)) {
-                    float q[3], v[3], sn[3], cs[3];
-                    row_kinematics(p, y1[r], y2[r], q, v, sn, cs);
+                    f2 q[3], v[3], sn[3], cs[3];
+                    row_kinematics(p, y1[pr], y2[pr], q, v, sn, cs);
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
-                        if (e.q) e.q[((size_t)b * T + t) * 3 + k] = q[k];
-                        if (e.v) e.v[((size_t)b * T + t) * 3 + k] = v[k];
+                        if (e.q) e.q[((size_t)b * T + t) * 3 + k] = q[k].x;
+                        if (e.v) e.v[((size_t)b * T + t) * 3 + k] = v[k].x;
+                        if (t + 1 < T) {
+                            if (e.q) e.q[((size_t)b * T + t + 1) * 3 + k] = q[k].y;
+                            if (e.v) e.v[((size_t)b * T + t + 1) * 3 + k] = v[k].y;
+                        }
                     }
                 }
             }
@@ -474,14 +495,15 @@ __global__ void __launch_bounds__(NW * 32) fgd_eval_kernel(const __grid_constant
             __syncwarp();
             contract<LPT, R, KS, false>(kd, T, XA, XB, y1, y2);
             if (live) {
-                float g[R][3];
+                f2 g[R / 2][3];
                 backward_rows<R>(p, y1, y2, g);
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    const int t = G.gl * R + r;
-                    if (t < T) {
+                for (int pr = 0; pr < R / 2; ++pr) {
+                    const int t = G.gl * R + 2 * pr;
 #pragma unroll
-                        for (int k = 0; k < 3; ++k) e.grad[((size_t)b * T + t) * 3 + k] = g[r][k];
+                    for (int k = 0; k < 3; ++k) {
+                        if (t < T) e.grad[((size_t)b * T + t) * 3 + k] = g[pr][k].x;
+                        if (t + 1 < T) e.grad[((size_t)b * T + t + 1) * 3 + k] = g[pr][k].y;
                     }
                 }
             }
@@ -522,6 +544,30 @@ __global__ void fgd_argmin_kernel(int n_problems, int n_restarts, const float *_
         const size_t b = (size_t)prob * n_restarts + r;
         best_cost[prob] = fstate[b * FGD_FSTATE + FGD_F_TOC];
         best_index[prob] = index_offset + (int)b;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// initTrajectory (trajectory.py:73-78) as a rank-2 update: one thread per (b, t).
+//   s' = start J^-1, d' = (goal - start) J^-1,  alpha[b][t][j] = fma(w[t], d'[j], u[t] * s'[j])
+// HBM-bound: 12 B written per (b, t), 24 B read per trajectory.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fgd_init_kernel(int B, int T, const float *__restrict__ uw, const float *__restrict__ jinv,
+                                                       const float *__restrict__ start, const float *__restrict__ goal,
+                                                       float *__restrict__ alpha)
+{
+    const long long n = (long long)B * T;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(i / T), t = (int)(i - (long long)b * T);
+        const float s0 = start[b * 3], s1 = start[b * 3 + 1], s2 = start[b * 3 + 2];
+        const float e0 = goal[b * 3] - s0, e1 = goal[b * 3 + 1] - s1, e2 = goal[b * 3 + 2] - s2;
+        const float u = uw[t], w = uw[T + t];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const float sj = fmaf(s2, jinv[6 + j], fmaf(s1, jinv[3 + j], s0 * jinv[j]));
+            const float dj = fmaf(e2, jinv[6 + j], fmaf(e1, jinv[3 + j], e0 * jinv[j]));
+            alpha[i * 3 + j] = fmaf(w, dj, u * sj);
+        }
     }
 }
 

@@ -108,6 +108,27 @@ class Trajectory:
         alpha = np.ascontiguousarray(sol.reshape(T, B, 3).transpose(1, 0, 2))
         return alpha[0] if single else alpha
 
+    def init_basis(self):
+        """u = K^-1 1, w = K^-1 c (one FP32 LU, the solver initTrajectory uses) and J^-1: the
+        batch-shared pieces of the rank-2 form of trajectory.py:73-78."""
+        rhs = np.stack([np.ones_like(self.c), self.c], axis=1).astype(np.float32)
+        uw = np.linalg.solve(self.km, rhs).astype(np.float32)
+        return np.ascontiguousarray(uw[:, 0]), np.ascontiguousarray(uw[:, 1]), np.linalg.inv(self.jac).astype(np.float32)
+
+    def initTrajectoryDevice(self, start, goal):
+        """initTrajectory for start/goal already on the GPU: (B,3) CUDA tensors -> alpha (B,T,3) CUDA
+        tensor, no host round trip.  Rank-2 restatement (include/fgd_b200.h: fgd_init_trajectory);
+        the host ``initTrajectory`` stays the reference-faithful per-trajectory LU solve."""
+        import torch
+        if not getattr(self, "_init_basis_set", False):
+            self.handle.set_init_basis(*self.init_basis())
+            self._init_basis_set = True
+        start = start.to(torch.float32).reshape(-1, 3).contiguous()
+        goal = goal.to(torch.float32).reshape(-1, 3).contiguous()
+        alpha = torch.empty(start.shape[0], self.N_timesteps, 3, dtype=torch.float32, device=start.device)
+        self.handle.init_trajectory(int(start.shape[0]), start, goal, alpha)
+        return alpha
+
     # ------------------------------------------------------------------
     def _eval(self, alpha, obstacles, start_config, goal_config, lam_sg, lam_jl, lam_max, want):
         import torch

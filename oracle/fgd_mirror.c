@@ -10,6 +10,7 @@
  *   environment.py:32-58                 (obstacle cost / gradient)
  *   optimizer_BLS.py:126-213             (jit loop semantics)
  *   optimizer_GD.py:68-97,172-232        (single-level and dual loops)
+ *   trajectory.py:73-78                  (initTrajectory, rank-2 form: mirror_init)
  * with every floating-point operation written out explicitly (fmaf where a
  * fused multiply-add is meant, separate * and + elsewhere; compiled with
  * -ffp-contract=off) and every reduction performed in one fixed, documented
@@ -412,6 +413,24 @@ int mirror_optimize(const MirrorCfg *c, const float *K_in, const float *dK_in, c
         optimize_one(c, &d, K, dK, obs, alpha + (size_t)b * T * 3, start + b * 3, goal + b * 3,
                      fstate + (size_t)b * FS, istate + (size_t)b * IS, budget);
     free(Kt); free(dKt);
+    return 0;
+}
+
+/* Rank-2 restatement of Trajectory.initTrajectory (trajectory.py:73-78), the op order of
+ * fgd_init_kernel:  s' = start J^-1, d' = (goal - start) J^-1,
+ *   alpha[b][t][j] = fmaf(w[t], d'[j], u[t] * s'[j])   with u = K^-1 1, w = K^-1 c (inputs). */
+int mirror_init(int T, int B, const float *u, const float *w, const float *jinv, const float *start, const float *goal,
+                float *alpha)
+{
+    for (int b = 0; b < B; ++b) {
+        const float s0 = start[b * 3], s1 = start[b * 3 + 1], s2 = start[b * 3 + 2];
+        const float e0 = goal[b * 3] - s0, e1 = goal[b * 3 + 1] - s1, e2 = goal[b * 3 + 2] - s2;
+        for (int j = 0; j < 3; ++j) {
+            const float sj = fmaf(s2, jinv[6 + j], fmaf(s1, jinv[3 + j], s0 * jinv[j]));
+            const float dj = fmaf(e2, jinv[6 + j], fmaf(e1, jinv[3 + j], e0 * jinv[j]));
+            for (int t = 0; t < T; ++t) alpha[((size_t)b * T + t) * 3 + j] = fmaf(w[t], dj, u[t] * sj);
+        }
+    }
     return 0;
 }
 

@@ -49,6 +49,7 @@ def lib():
         _lib.mirror_eval.argtypes = [C.POINTER(MirrorCfg), fp, fp, fp, C.c_int, fp, fp, fp, C.c_float, C.c_float,
                                      fp, fp, fp, fp, fp, ip]
         _lib.mirror_optimize.argtypes = [C.POINTER(MirrorCfg), fp, fp, fp, C.c_int, fp, fp, fp, fp, ip, C.c_int, C.c_int]
+        _lib.mirror_init.argtypes = [C.c_int, C.c_int, fp, fp, fp, fp, fp, fp]
         _lib.mirror_max_threads.restype = C.c_int
     return _lib
 
@@ -134,6 +135,20 @@ class Mirror:
         if rc:
             raise RuntimeError(f"mirror_optimize rc={rc}")
         return alpha, fstate, istate
+
+
+def init_trajectory(u, w, jinv, start, goal) -> np.ndarray:
+    """Rank-2 initTrajectory (trajectory.py:73-78) in the device kernel's op order."""
+    u, w = np.ascontiguousarray(u, np.float32), np.ascontiguousarray(w, np.float32)
+    jinv = np.ascontiguousarray(jinv, np.float32).reshape(9)
+    start = np.ascontiguousarray(start, np.float32).reshape(-1, 3)
+    goal = np.ascontiguousarray(goal, np.float32).reshape(-1, 3)
+    B, T = start.shape[0], u.shape[0]
+    alpha = np.empty((B, T, 3), np.float32)
+    rc = lib().mirror_init(T, B, _fp(u), _fp(w), _fp(jinv), _fp(start), _fp(goal), _fp(alpha))
+    if rc:
+        raise RuntimeError(f"mirror_init rc={rc}")
+    return alpha
 
 
 def max_threads() -> int:

@@ -330,6 +330,47 @@ __device__ __forceinline__ void row_kinematics(const DevParams &p, const f2 (&yq
     sincos_cw2(c3, sn[2], cs[2]);
 }
 
+// U obstacles against RP row pairs (environment.py:32-58): sr += 1/den, sx += dx/den^2, sy += dy/den^2
+// with den = 0.5 + 0.5 |f - o|^2.
+template <int RP, int U, bool STRICT>
+__device__ __forceinline__ void obstacle_block(const float2 *__restrict__ obs, const f2 (&x)[RP], const f2 (&y)[RP],
+                                               f2 (&sr)[RP], f2 (&sx)[RP], f2 (&sy)[RP])
+{
+    float2 ob[U];
+    if constexpr (U == 4) {
+        const float4 a = *reinterpret_cast<const float4 *>(obs), b = *reinterpret_cast<const float4 *>(obs + 2);
+        ob[0] = make_float2(a.x, a.y); ob[1] = make_float2(a.z, a.w); ob[2] = make_float2(b.x, b.y); ob[3] = make_float2(b.z, b.w);
+    } else if constexpr (U == 2) {
+        const float4 a = *reinterpret_cast<const float4 *>(obs);
+        ob[0] = make_float2(a.x, a.y); ob[1] = make_float2(a.z, a.w);
+    } else {
+        ob[0] = obs[0];
+    }
+    f2 dx[U][RP], dy[U][RP], rr[U][RP];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int pr = 0; pr < RP; ++pr) {
+            dx[u][pr] = add2(x[pr], bc2(-ob[u].x));
+            dy[u][pr] = add2(y[pr], bc2(-ob[u].y));
+            const f2 n = fma2(dy[u][pr], dy[u][pr], mul2(dx[u][pr], dx[u][pr]));
+            rr[u][pr] = fma2(bc2(0.5f), n, bc2(0.5f));
+        }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int pr = 0; pr < RP; ++pr) rr[u][pr] = mk2(rcp<STRICT>(rr[u][pr].x), rcp<STRICT>(rr[u][pr].y));
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int pr = 0; pr < RP; ++pr) {
+            sr[pr] = add2(sr[pr], rr[u][pr]);
+            const f2 r2 = mul2(rr[u][pr], rr[u][pr]);
+            sx[pr] = fma2(r2, dx[u][pr], sx[pr]);
+            sy[pr] = fma2(r2, dy[u][pr], sy[pr]);
+        }
+}
+
 // ---------------------------------------------------------------------------
 // Cost phase: compute_trajectory_cost + constraintsFulfilled for one trajectory
 // whose raw contraction rows are yq (K alpha) and yv (dK alpha).
@@ -402,25 +443,20 @@ __device__ __forceinline__ void cost_phase(const DevParams &p, const float2 *__r
             ssvT = ss3(v[0].y, v[1].y, v[2].y);
         }
     }
-    // obstacle potential: all R samples of this lane against every obstacle
+    // obstacle potential: all R samples of this lane against every obstacle, in blocks of U obstacles.
+    // Each block runs in three stages (distances -> reciprocals -> accumulation) so that U * R/2
+    // independent packed chains are in flight across the MUFU latency; the accumulation stage
+    // visits the obstacles in ascending order (the oracle's summation order).
     const int n_obs = p.n_obs;
-    constexpr int OBS_UNROLL = (R >= 8) ? 1 : ((R == 4) ? 2 : 4);      // R/2 independent packed chains per obstacle already
-    float2 ob_next = sObs[0];                       // software pipelining: the next obstacle is fetched one trip ahead
-#pragma unroll OBS_UNROLL
-    for (int o = 0; o < n_obs; ++o) {
-        const float2 ob = ob_next;
-        ob_next = sObs[o + 1];                      // the buffer is padded by one pair (make_layout)
-#pragma unroll
-        for (int pr = 0; pr < RP; ++pr) {
-            const f2 dx = add2(x[pr], bc2(-ob.x)), dy = add2(y[pr], bc2(-ob.y));
-            const f2 n = fma2(dy, dy, mul2(dx, dx));
-            const f2 den = fma2(bc2(0.5f), n, bc2(0.5f));
-            const f2 rr = mk2(rcp<STRICT>(den.x), rcp<STRICT>(den.y));
-            sr[pr] = add2(sr[pr], rr);
-            const f2 r2 = mul2(rr, rr);
-            sx[pr] = fma2(r2, dx, sx[pr]);
-            sy[pr] = fma2(r2, dy, sy[pr]);
-        }
+    constexpr int U = (R >= 8) ? 1 : ((R == 4) ? 2 : 4);
+    int o = 0;
+#pragma unroll 1
+    for (; o + U <= n_obs; o += U) obstacle_block<RP, U, STRICT>(sObs + o, x, y, sr, sx, sy);
+    if constexpr (U >= 4) {
+        if (o + 2 <= n_obs) { obstacle_block<RP, 2, STRICT>(sObs + o, x, y, sr, sx, sy); o += 2; }
+    }
+    if constexpr (U >= 2) {
+        if (o < n_obs) obstacle_block<RP, 1, STRICT>(sObs + o, x, y, sr, sx, sy);
     }
     f2 cost[RP];
 #pragma unroll

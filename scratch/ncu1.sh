@@ -1,0 +1,10 @@
+#!/bin/bash
+mkdir -p gpurun_out
+W=${1:-c2}; B=${2:-65536}; TAG=${3:-r01b_c2_b65536}
+python bench.py --workload $W --batch $B --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_plain.log 2>&1 || exit 1
+ncu --set full --clock-control none --import-source on -k regex:fgd_optimize_kernel -s 1 -c 1 -o gpurun_out/${TAG} -f python bench.py --workload $W --batch $B --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_ncu.log 2>&1
+ncu -i gpurun_out/${TAG}.ncu-rep --page details > gpurun_out/${TAG}_details.txt 2>&1
+ncu -i gpurun_out/${TAG}.ncu-rep --page source --csv > gpurun_out/${TAG}_source.csv 2>&1
+ncu -i gpurun_out/${TAG}.ncu-rep --page raw --csv > gpurun_out/${TAG}_raw.csv 2>&1
+rm -f gpurun_out/${TAG}.ncu-rep
+tail -2 gpurun_out/${TAG}_ncu.log

@@ -239,6 +239,22 @@ def test_result_independent_of_batch_position(cuda_ready):
     assert (ar.cpu().numpy() == ar.cpu().numpy()[0]).all() and (isr.cpu().numpy() == isr.cpu().numpy()[0]).all()
 
 
+@pytest.mark.parametrize("T,B", [(50, 1), (50, 4097), (256, 300)])
+def test_device_init_trajectory_bit_exact_and_optimisable(cuda_ready, T, B):
+    """fgd_init_trajectory == oracle mirror_init bit for bit; optimising from the
+    device-initialised alpha is bit-identical to the oracle optimising from the oracle's init."""
+    import torch
+    args, tr, obs, start, goal, _ = _setup(T=T, B=B, seed=5)
+    s, g = torch.as_tensor(start, device="cuda"), torch.as_tensor(goal, device="cuda")
+    a_dev = tr.initTrajectoryDevice(s, g)
+    a_ref = M.init_trajectory(*tr.init_basis(), start, goal)
+    assert np.array_equal(a_dev.cpu().numpy(), a_ref)
+    if B <= 300 and T == 50:
+        a, fs, is_ = _gpu_optimize(tr, "bls", a_dev, start, goal)
+        ca, cfs, cis = _mirror(args, tr, obs, "bls").optimize(a_ref, start, goal)
+        assert np.array_equal(is_.cpu().numpy(), cis) and np.array_equal(a.cpu().numpy(), ca)
+
+
 def test_argmin_per_problem(cuda_ready):
     import torch
     from irm_motion_planning_b200.batch import BatchedFGD, BatchResult

@@ -175,3 +175,25 @@ def test_dynamic_obstacles_schedule(tm):
             a, fs, is_ = m.optimize(a, START, GOAL, fs, is_, budget=1)
             lrs.append(float(fs[0, M.F_LR]) / 1.2)
     np.testing.assert_allclose(lrs[:8], log.lrs[:8], rtol=1e-6)
+
+
+@pytest.mark.parametrize("T", [50, 128, 256])
+def test_rank2_init_reproduces_the_reference_line_fit(T):
+    """the rank-2 initTrajectory (mirror_init, the op order of fgd_init_kernel) and the
+    reference-faithful per-trajectory LU solve (trajectory.py:73-78) fit the same straight line:
+    both K alpha J are within 5e-3 rad of it (FP32 LU residual on a numerically singular K; the
+    alphas themselves are rounding noise of size ~3e3) and obey q(0)=start, q(1)=goal."""
+    from irm_motion_planning_b200.trajectory import Trajectory
+    from irm_motion_planning_b200.workloads import default_args, sample_start_goal
+    tr = Trajectory(default_args(n_timesteps=float(T)), create_handle=False)
+    s, g = sample_start_goal(32, np.random.default_rng(T))
+    a_rank2 = M.init_trajectory(*tr.init_basis(), s, g)
+    a_lu = tr.initTrajectory(s, g)
+    line = s[:, None, :] + (g - s)[:, None, :] * tr.c[None, :, None]
+    K, J = tr.km.astype(np.float64), tr.jac.astype(np.float64)
+    for a in (a_rank2, a_lu):
+        q = K @ a.astype(np.float64) @ J
+        assert np.abs(q - line).max() < 5e-3
+    # linearity: the rank-2 form is exactly linear in (start, goal) up to rounding
+    a2 = M.init_trajectory(*tr.init_basis(), 2 * s, 2 * g)
+    assert np.allclose(a2, 2 * a_rank2, rtol=1e-5, atol=1e-3)

@@ -162,7 +162,7 @@ int fgd_init_trajectory(FgdHandle *h, int32_t B, const float *d_start, const flo
 
 /* Introspection for the harness. */
 int fgd_launch_geometry(const FgdHandle *h, int32_t B, int32_t *grid, int32_t *block, int32_t *smem_bytes,
-                        int32_t *trajectories_per_warp);
+                        int32_t *warps_per_trajectory);
 int64_t fgd_kernel_launches(const FgdHandle *h);   /* kernels launched through this handle so far */
 /* FP32 FFMA throughput of the current device (TFLOP/s, best of 5 launches of a
  * pure-FFMA kernel): the measured denominator of the harness's roofline.frac. */

@@ -245,7 +245,7 @@ class Handle:
         g, b, s, t = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
         self._check(self._lib.fgd_launch_geometry(self._h, B, C.byref(g), C.byref(b), C.byref(s), C.byref(t)),
                     "fgd_launch_geometry")
-        return dict(grid=g.value, block=b.value, smem_bytes=s.value, trajectories_per_warp=t.value)
+        return dict(grid=g.value, block=b.value, smem_bytes=s.value, warps_per_trajectory=t.value)
 
     def measure_fp32_peak(self) -> float:
         out = C.c_double()

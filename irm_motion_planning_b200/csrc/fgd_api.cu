@@ -14,7 +14,7 @@ using namespace fgd;
 struct FgdHandle {
     FgdConfig cfg;
     DevParams base;            // everything except the per-call batch pointers
-    int T, TP, LPT, R, variant = 0;
+    int T, TP, WPT, variant = 0;
     bool k_in_smem;
     int device, num_sms, max_smem_optin;
     float *d_KD = nullptr, *d_KO = nullptr;
@@ -41,95 +41,91 @@ struct FgdHandle {
 
 namespace {
 
-struct Geometry { int gpw, grid, block, smem; };
+struct Geometry { int grid, block, smem; };
 
-// lane mapping by trajectory length: LPT lanes per trajectory, R adjacent rows per lane (TP = LPT*R >= T)
-struct Mapping { int LPT, R; };
-inline Mapping mapping_for(int T) { return T <= 64 ? Mapping{32, 2} : (T <= 128 ? Mapping{32, 4} : Mapping{32, 8}); }
+// warps per trajectory by trajectory length (each thread owns R = 2 adjacent time samples: TP = 64 * WPT >= T)
+inline int warps_per_trajectory(int T) { return T <= 64 ? 1 : (T <= 128 ? 2 : 4); }
 
-// (variant, LPT, R, KS, NW, MINB, LEAN): the instantiated kernels.  KS: K tables staged in shared memory
-// (T <= 64) or read from L2; NW warps per CTA, MINB = min CTAs per SM (register cap); LEAN: alpha/direction
-// rows in shared memory and kinematics recomputed in the gradient phase (large T).  Variant 0 is the default;
-// the others exist for tuning (env FGD_VARIANT).
+// (variant, WPT, KS, NW, MINB): the instantiated kernels.  WPT warps per trajectory; KS: K tables staged in
+// shared memory (T <= 64) or read from L2; NW warps per CTA (= WPT for multi-warp teams), MINB = min CTAs
+// per SM (register cap).  Variant 0 is the default; the others exist for tuning (env FGD_VARIANT).
 #define FGD_FOR_CONFIGS(X) \
-    X(0, 32, 2, true, 8, 2, false) X(0, 32, 4, false, 4, 4, true) X(0, 32, 8, false, 4, 2, true) \
-    X(1, 32, 2, true, 4, 4, false) X(1, 32, 8, false, 4, 3, true) X(2, 32, 8, false, 8, 1, true)
+    X(0, 1, true, 8, 2) X(0, 2, false, 2, 8) X(0, 4, false, 4, 4) \
+    X(1, 1, true, 4, 4) X(1, 2, false, 2, 6) X(1, 4, false, 4, 3)
 
-template <int LPT, int R, bool STRICT, bool KS, int NW, int MINB, bool LEAN>
+template <int WPT, bool STRICT, bool KS, int NW, int MINB>
 cudaError_t launch_opt(const DevParams &p, int grid, size_t smem, cudaStream_t st)
 {
-    auto kern = fgd_optimize_kernel<LPT, R, STRICT, KS, NW, MINB, LEAN>;
+    auto kern = fgd_optimize_kernel<WPT, STRICT, KS, NW, MINB>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, NW * 32, smem, st>>>(p);
     return cudaGetLastError();
 }
 
-template <int LPT, int R, bool STRICT, bool KS, int NW, int MINB, bool LEAN>
+template <int WPT, bool STRICT, bool KS, int NW, int MINB>
 int occupancy_opt(size_t smem)
 {
-    auto kern = fgd_optimize_kernel<LPT, R, STRICT, KS, NW, MINB, LEAN>;
+    auto kern = fgd_optimize_kernel<WPT, STRICT, KS, NW, MINB>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int nb = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, NW * 32, smem) != cudaSuccess) nb = 1;
     return nb < 1 ? 1 : nb;
 }
 
-template <int LPT, int R, bool STRICT, bool KS, int NW>
+template <int WPT, bool STRICT, bool KS, int NW>
 cudaError_t launch_eval(const DevParams &p, const EvalPtrs &e, int grid, size_t smem, cudaStream_t st)
 {
-    auto kern = fgd_eval_kernel<LPT, R, STRICT, KS, NW>;
+    auto kern = fgd_eval_kernel<WPT, STRICT, KS, NW>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     kern<<<grid, NW * 32, smem, st>>>(p, e);
     return cudaGetLastError();
 }
 
-int g_variant = 0;
-
-bool variant_exists(int v, int LPT, int R)
+bool variant_exists(int v, int WPT)
 {
-#define X(V_, L_, R_, KS_, NW_, MB_, LN_) if (v == V_ && LPT == L_ && R == R_) return true;
+#define X(V_, W_, KS_, NW_, MB_) if (v == V_ && WPT == W_) return true;
     FGD_FOR_CONFIGS(X)
 #undef X
     return false;
 }
 
-int warps_per_cta(int v, int LPT, int R)
+int warps_per_cta(int v, int WPT)
 {
-#define X(V_, L_, R_, KS_, NW_, MB_, LN_) if (v == V_ && LPT == L_ && R == R_) return NW_;
+#define X(V_, W_, KS_, NW_, MB_) if (v == V_ && WPT == W_) return NW_;
     FGD_FOR_CONFIGS(X)
 #undef X
-    return 4;
+    return WPT;
 }
 
-cudaError_t dispatch_opt(int v, int LPT, int R, bool strict, const DevParams &p, int grid, size_t smem, cudaStream_t st)
+cudaError_t dispatch_opt(int v, int WPT, bool strict, const DevParams &p, int grid, size_t smem, cudaStream_t st)
 {
-#define X(V_, L_, R_, KS_, NW_, MB_, LN_)                                                    \
-    if (v == V_ && LPT == L_ && R == R_)                                                      \
-        return strict ? launch_opt<L_, R_, true, KS_, NW_, MB_, LN_>(p, grid, smem, st)       \
-                      : launch_opt<L_, R_, false, KS_, NW_, MB_, LN_>(p, grid, smem, st);
+#define X(V_, W_, KS_, NW_, MB_)                                                        \
+    if (v == V_ && WPT == W_)                                                            \
+        return strict ? launch_opt<W_, true, KS_, NW_, MB_>(p, grid, smem, st)           \
+                      : launch_opt<W_, false, KS_, NW_, MB_>(p, grid, smem, st);
     FGD_FOR_CONFIGS(X)
 #undef X
     return cudaErrorInvalidValue;
 }
 
-int dispatch_occ(int v, int LPT, int R, bool strict, size_t smem)
+int dispatch_occ(int v, int WPT, bool strict, size_t smem)
 {
-#define X(V_, L_, R_, KS_, NW_, MB_, LN_)                                                    \
-    if (v == V_ && LPT == L_ && R == R_)                                                      \
-        return strict ? occupancy_opt<L_, R_, true, KS_, NW_, MB_, LN_>(smem) : occupancy_opt<L_, R_, false, KS_, NW_, MB_, LN_>(smem);
+#define X(V_, W_, KS_, NW_, MB_)                                                        \
+    if (v == V_ && WPT == W_)                                                            \
+        return strict ? occupancy_opt<W_, true, KS_, NW_, MB_>(smem) : occupancy_opt<W_, false, KS_, NW_, MB_>(smem);
     FGD_FOR_CONFIGS(X)
 #undef X
     return 1;
 }
 
-cudaError_t dispatch_eval(int LPT, int R, bool strict, const DevParams &p, const EvalPtrs &e, int grid, size_t smem, cudaStream_t st)
+cudaError_t dispatch_eval(int WPT, bool strict, const DevParams &p, const EvalPtrs &e, int grid, size_t smem, cudaStream_t st)
 {
-#define X(V_, L_, R_, KS_, NW_, MB_, LN_)                                                    \
-    if (V_ == 0 && LPT == L_ && R == R_)                                                      \
-        return strict ? launch_eval<L_, R_, true, KS_, NW_>(p, e, grid, smem, st)             \
-                      : launch_eval<L_, R_, false, KS_, NW_>(p, e, grid, smem, st);
+#define X(V_, W_, KS_, NW_, MB_)                                                        \
+    if (V_ == 0 && WPT == W_)                                                            \
+        return strict ? launch_eval<W_, true, KS_, NW_>(p, e, grid, smem, st)            \
+                      : launch_eval<W_, false, KS_, NW_>(p, e, grid, smem, st);
     FGD_FOR_CONFIGS(X)
 #undef X
     return cudaErrorInvalidValue;
@@ -138,13 +134,12 @@ cudaError_t dispatch_eval(int LPT, int R, bool strict, const DevParams &p, const
 Geometry geometry(const FgdHandle *h, int B, int n_obs)
 {
     Geometry g;
-    const int nw = warps_per_cta(h->variant, h->LPT, h->R);
-    g.gpw = 32 / h->LPT;
+    const int nw = warps_per_cta(h->variant, h->WPT);
+    const int teams = nw / h->WPT;
     g.block = nw * 32;
-    g.smem = (int)make_layout(h->T, h->TP, n_obs, h->k_in_smem, nw * g.gpw, h->R > 2).bytes();
-    const int occ = dispatch_occ(h->variant, h->LPT, h->R, h->cfg.strict_math != 0, (size_t)g.smem);
-    const long long per_cta = (long long)nw * g.gpw;
-    const long long need = ((long long)B + per_cta - 1) / per_cta;
+    g.smem = (int)make_layout(h->T, h->TP, n_obs, h->k_in_smem, teams, h->WPT).bytes();
+    const int occ = dispatch_occ(h->variant, h->WPT, h->cfg.strict_math != 0, (size_t)g.smem);
+    const long long need = ((long long)B + teams - 1) / teams;
     const long long cap = (long long)occ * h->num_sms;
     g.grid = (int)(need < cap ? need : cap);
     if (g.grid < 1) g.grid = 1;
@@ -183,7 +178,7 @@ int run_optimize(FgdHandle *h, int mode, int B, float *d_alpha, const float *d_s
     fill_params(h, p, mode, B, d_alpha, d_start, d_goal, d_fstate, d_istate, budget);
     const Geometry g = geometry(h, B, p.n_obs);
     CK(cudaMemsetAsync(h->d_queue, 0, sizeof(unsigned), st));
-    CK(dispatch_opt(h->variant, h->LPT, h->R, h->cfg.strict_math != 0, p, g.grid, (size_t)g.smem, st));
+    CK(dispatch_opt(h->variant, h->WPT, h->cfg.strict_math != 0, p, g.grid, (size_t)g.smem, st));
     h->launches += 1;
     CK(cudaEventRecord(h->launch_event, st));
     h->launch_event_pending = true;
@@ -238,27 +233,28 @@ int fgd_create(const FgdConfig *cfg, FgdHandle **out)
     h->cfg = *cfg;
     h->cfg.h_km = nullptr; h->cfg.h_dkm = nullptr;
     h->T = T;
-    { const Mapping m = mapping_for(T); h->LPT = m.LPT; h->R = m.R; }
-    h->TP = h->LPT * h->R;
+    h->WPT = warps_per_trajectory(T);
+    h->TP = h->WPT * 32 * R;
     auto fail = [&](int code) { fgd_destroy(h); return code; };
 #define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(FGD_ERR_CUDA); } while (0)
     CKC(cudaGetDevice(&h->device));
     CKC(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device));
     CKC(cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
     // K and dK go to shared memory when both fit beside the operand buffers of at least one slot per warp
-    if (const char *e = std::getenv("FGD_VARIANT")) { const int v = std::atoi(e); if (variant_exists(v, h->LPT, h->R)) h->variant = v; }
-    h->k_in_smem = h->R == 2;     // T <= 64: 3*T*64*4 B <= 48 KB per CTA; larger T reads the K tables from L2
+    if (const char *e = std::getenv("FGD_VARIANT")) { const int v = std::atoi(e); if (variant_exists(v, h->WPT)) h->variant = v; }
+    h->k_in_smem = h->WPT == 1;   // T <= 64: 3*T*64*4 B <= 48 KB per CTA; larger T reads the K tables from L2
 
-    // operand table KD[k][lane][2R]: the R row entries K[t][k] then the R entries dK[t][k] of lane's rows t = R*lane + r
-    // and KO[k][lane][R]: the K entries alone (dense half of the backward contraction)
+    // operand table KD[k][thread][2R]: the R row entries K[t][k] then the R entries dK[t][k] of the team thread's rows
+    // t = R*thread + r, and KO[k][thread][R]: the K entries alone (dense half of the backward contraction)
+    const int nthr = h->TP / R;
     std::vector<float> kd((size_t)T * 2 * h->TP, 0.0f), ko((size_t)T * h->TP, 0.0f);
     for (int k = 0; k < T; ++k)
         for (int i = 0; i < T; ++i) {
-            const int lane = i / h->R, r = i % h->R;
-            const size_t base = ((size_t)k * h->LPT + lane) * 2 * h->R;
+            const int thr = i / R, r = i % R;
+            const size_t base = ((size_t)k * nthr + thr) * 2 * R;
             kd[base + r] = cfg->h_km[i * T + k];
-            kd[base + h->R + r] = cfg->h_dkm[i * T + k];
-            ko[((size_t)k * h->LPT + lane) * h->R + r] = cfg->h_km[i * T + k];
+            kd[base + R + r] = cfg->h_dkm[i * T + k];
+            ko[((size_t)k * nthr + thr) * R + r] = cfg->h_km[i * T + k];
         }
     CKC(cudaMalloc(&h->d_KD, kd.size() * 4));
     CKC(cudaMemcpy(h->d_KD, kd.data(), kd.size() * 4, cudaMemcpyHostToDevice));
@@ -356,11 +352,11 @@ int fgd_eval_cost_grad(FgdHandle *h, int32_t B, const float *d_alpha, const floa
         p.lam_max = lambda_max_cost; p.oml = 1.0f - p.lam_max; p.w_avg = p.oml * p.inv_T;
     }
     EvalPtrs e{lambda_sg, lambda_jl, d_loss, d_toc, d_grad, d_q, d_v, d_fulfilled};
-    const int nw = warps_per_cta(0, h->LPT, h->R), per_cta = nw * (32 / h->LPT);
-    const size_t smem = make_layout(h->T, h->TP, p.n_obs, h->k_in_smem, per_cta, false).bytes();
+    const int nw = warps_per_cta(0, h->WPT), per_cta = nw / h->WPT;
+    const size_t smem = make_layout(h->T, h->TP, p.n_obs, h->k_in_smem, per_cta, h->WPT).bytes();
     long long need = ((long long)B + per_cta - 1) / per_cta, cap = (long long)h->num_sms * 4;
     const int grid = (int)(need < cap ? need : cap);
-    CK(dispatch_eval(h->LPT, h->R, h->cfg.strict_math != 0, p, e, grid, smem, st));
+    CK(dispatch_eval(h->WPT, h->cfg.strict_math != 0, p, e, grid, smem, st));
     h->launches += 1;
     return FGD_OK;
 }
@@ -447,14 +443,14 @@ int fgd_init_trajectory(FgdHandle *h, int32_t B, const float *d_start, const flo
     return FGD_OK;
 }
 
-int fgd_launch_geometry(const FgdHandle *h, int32_t B, int32_t *grid, int32_t *block, int32_t *smem_bytes, int32_t *traj_per_warp)
+int fgd_launch_geometry(const FgdHandle *h, int32_t B, int32_t *grid, int32_t *block, int32_t *smem_bytes, int32_t *warps_per_trajectory)
 {
     if (!h || B < 1) return FGD_ERR_INVALID_ARGUMENT;
     const Geometry g = geometry(h, B, h->obs_count);
     if (grid) *grid = g.grid;
     if (block) *block = g.block;
     if (smem_bytes) *smem_bytes = g.smem;
-    if (traj_per_warp) *traj_per_warp = g.gpw;
+    if (warps_per_trajectory) *warps_per_trajectory = h->WPT;
     return FGD_OK;
 }
 

@@ -23,86 +23,51 @@ struct SmemLayout {
     int k_floats;     // T*TP when the K tables are staged in shared memory (KD = 2x, KO = 1x), 0 when they stay in L2
     int obs_pairs;    // obstacle slots (padded to even)
     int x_rows;       // float4 rows per operand buffer
-    int ad_rows;      // float4 slots per alpha / direction buffer (LEAN variants keep them in shared memory, lane-major)
-    int n_groups;     // trajectory groups per CTA
-    __host__ __device__ size_t bytes() const
-    {
-        return (size_t)3 * k_floats * 4 + (size_t)obs_pairs * 8 + (size_t)n_groups * 2 * (x_rows + ad_rows) * 16;
-    }
+    int n_teams;      // trajectory teams per CTA
+    int xch_words;    // exchange scratch words per team (0 for single-warp teams)
+    __host__ __device__ size_t team_bytes() const { return (size_t)2 * x_rows * 16 + (size_t)xch_words * 4; }
+    __host__ __device__ size_t bytes() const { return (size_t)3 * k_floats * 4 + (size_t)obs_pairs * 8 + (size_t)n_teams * team_bytes(); }
 };
 
-__host__ __device__ inline SmemLayout make_layout(int T, int TP, int n_obs, bool ks, int n_groups, bool lean)
+__host__ __device__ inline SmemLayout make_layout(int T, int TP, int n_obs, bool ks, int n_teams, int wpt)
 {
     SmemLayout l;
     l.k_floats = ks ? T * TP : 0;
-    l.obs_pairs = (n_obs + 2) & ~1;     // >= n_obs + 1: the obstacle loop prefetches one pair ahead
-    l.x_rows = T | 1;     // odd row count: the operand buffers of neighbouring groups start 4 banks apart (mod 8)
-    l.ad_rows = lean ? TP : 0;
-    l.n_groups = n_groups;
+    l.obs_pairs = (n_obs + 2) & ~1;
+    l.x_rows = T | 1;     // odd row count: the operand buffers of neighbouring teams start 4 banks apart (mod 8)
+    l.n_teams = n_teams;
+    l.xch_words = wpt > 1 ? XCH_WORDS : 0;
     return l;
-}
-
-// lane-major row store: slot (r, lane) -> buf[r * 32 + lane]   (conflict-free for a warp)
-template <int R>
-__device__ __forceinline__ void ld_rows(const float4 *buf, int lane, f2 (&x)[R / 2][3])
-{
-#pragma unroll
-    for (int pr = 0; pr < R / 2; ++pr) {
-        const float4 u = buf[(2 * pr) * 32 + lane], v = buf[(2 * pr + 1) * 32 + lane];
-        x[pr][0] = mk2(u.x, v.x); x[pr][1] = mk2(u.y, v.y); x[pr][2] = mk2(u.z, v.z);
-    }
-}
-template <int R>
-__device__ __forceinline__ void st_rows(float4 *buf, int lane, const f2 (&x)[R / 2][3])
-{
-#pragma unroll
-    for (int pr = 0; pr < R / 2; ++pr) {
-        buf[(2 * pr) * 32 + lane] = make_float4(x[pr][0].x, x[pr][1].x, x[pr][2].x, 0.0f);
-        buf[(2 * pr + 1) * 32 + lane] = make_float4(x[pr][0].y, x[pr][1].y, x[pr][2].y, 0.0f);
-    }
 }
 
 __device__ __forceinline__ void hash_step(Slot &st, unsigned code) { st.hash = st.hash * 1000003u + code; }
 
+// rows of this thread (alpha, a candidate, ...) into an operand buffer
+template <int WPT>
+__device__ __forceinline__ void write_rows(const DevParams &p, const Team<WPT> &G, const f2 (&c)[3], float4 *X)
+{
+    const int t = G.tl * R;
+    if (t < p.T) X[t] = make_float4(c[0].x, c[1].x, c[2].x, 0.0f);
+    if (t + 1 < p.T) X[t + 1] = make_float4(c[0].y, c[1].y, c[2].y, 0.0f);
+}
+
 // candidate  (1 - lam_reg*lr) * alpha - lr * dir      optimizer_BLS.py:139, optimizer_GD.py:185
-template <int LPT, int R>
-__device__ __forceinline__ void write_candidate(const DevParams &p, const Group<LPT> &G, float lr, const f2 (&a)[R / 2][3],
-                                                const f2 (&d)[R / 2][3], float4 *XA)
+__device__ __forceinline__ void make_candidate(const DevParams &p, float lr, const f2 (&a)[3], const f2 (&d)[3], f2 (&c)[3])
 {
     const float c1 = 1.0f - p.lam_reg * lr;
 #pragma unroll
-    for (int pr = 0; pr < R / 2; ++pr) {
-        const int t = G.gl * R + 2 * pr;
-        f2 c[3];
-#pragma unroll
-        for (int b = 0; b < 3; ++b) c[b] = fma2(bc2(c1), a[pr][b], neg2(mul2(bc2(lr), d[pr][b])));
-        if (t < p.T) XA[t] = make_float4(c[0].x, c[1].x, c[2].x, 0.0f);
-        if (t + 1 < p.T) XA[t + 1] = make_float4(c[0].y, c[1].y, c[2].y, 0.0f);
-    }
+    for (int b = 0; b < 3; ++b) c[b] = fma2(bc2(c1), a[b], neg2(mul2(bc2(lr), d[b])));
 }
 
-template <int R>
-__device__ __forceinline__ void accept_candidate(const DevParams &p, float lr, f2 (&a)[R / 2][3], const f2 (&d)[R / 2][3])
-{
-    const float c1 = 1.0f - p.lam_reg * lr;
-#pragma unroll
-    for (int pr = 0; pr < R / 2; ++pr)
-#pragma unroll
-        for (int b = 0; b < 3; ++b) a[pr][b] = fma2(bc2(c1), a[pr][b], neg2(mul2(bc2(lr), d[pr][b])));
-}
-
-template <int LPT, int R>
-__device__ __forceinline__ void save_slot(const DevParams &p, const Group<LPT> &G, const Slot &st, int status, const f2 (&a)[R / 2][3])
+template <int WPT>
+__device__ __forceinline__ void save_slot(const DevParams &p, const Team<WPT> &G, const Slot &st, int status, const f2 (&a)[3])
 {
     const int b = st.traj;
     float *ap = p.alpha + (size_t)b * p.T * 3;
-#pragma unroll
-    for (int pr = 0; pr < R / 2; ++pr) {
-        const int t = G.gl * R + 2 * pr;
-        if (t < p.T) { ap[t * 3] = a[pr][0].x; ap[t * 3 + 1] = a[pr][1].x; ap[t * 3 + 2] = a[pr][2].x; }
-        if (t + 1 < p.T) { ap[t * 3 + 3] = a[pr][0].y; ap[t * 3 + 4] = a[pr][1].y; ap[t * 3 + 5] = a[pr][2].y; }
-    }
-    if (G.gl == 0) {
+    const int t = G.tl * R;
+    if (t < p.T) { ap[t * 3] = a[0].x; ap[t * 3 + 1] = a[1].x; ap[t * 3 + 2] = a[2].x; }
+    if (t + 1 < p.T) { ap[t * 3 + 3] = a[0].y; ap[t * 3 + 4] = a[1].y; ap[t * 3 + 5] = a[2].y; }
+    if (G.tl == 0) {
         float *fs = p.fstate + (size_t)b * FGD_FSTATE;
         int *is = p.istate + (size_t)b * FGD_ISTATE;
         fs[FGD_F_LAM_SG] = st.lam_sg; fs[FGD_F_LAM_JL] = st.lam_jl; fs[FGD_F_LR] = st.lr;
@@ -113,72 +78,51 @@ __device__ __forceinline__ void save_slot(const DevParams &p, const Group<LPT> &
     }
 }
 
-// Start (or restart after a lambda increase / a resumed launch) with the loss and
-// gradient operands at the current alpha: optimizer_BLS.py:163, optimizer_GD.py:210.
-template <int LPT, int R>
-__device__ __forceinline__ void begin_outer_eval(const DevParams &p, const Group<LPT> &G, Slot &st, int &kind, const f2 (&a)[R / 2][3], float4 *XA)
-{
-    if (p.mode == 1) st.lr = p.gd_lr[st.outer];
-#pragma unroll
-    for (int pr = 0; pr < R / 2; ++pr) {
-        const int t = G.gl * R + 2 * pr;
-        if (t < p.T) XA[t] = make_float4(a[pr][0].x, a[pr][1].x, a[pr][2].x, 0.0f);
-        if (t + 1 < p.T) XA[t + 1] = make_float4(a[pr][0].y, a[pr][1].y, a[pr][2].y, 0.0f);
-    }
-    kind = K_EVAL0;
-}
-
-// Pull the next unfinished trajectory from the batch queue into every group that asks for one.
-// Executed by the whole (converged) warp; `need` is group-uniform.
-template <int LPT, int R>
-__device__ __forceinline__ void fetch_slot(const DevParams &p, const Group<LPT> &G, bool need, Slot &st, int &kind, f2 (&a)[R / 2][3])
+// Pull the next unfinished trajectory from the batch queue (team-uniform).
+template <int WPT>
+__device__ __forceinline__ void fetch_slot(const DevParams &p, const Team<WPT> &G, Slot &st, int &kind, f2 (&a)[3])
 {
     for (;;) {
-        __syncwarp();
-        if (!__any_sync(FULL, need)) break;
         unsigned idx = 0;
-        if (need && G.gl == 0) idx = atomicAdd(p.queue, 1u);
-        __syncwarp();
-        idx = __shfl_sync(FULL, idx, 0, LPT);
-        if (need) {
-            if (idx >= (unsigned)p.B) {
-                st.traj = -1; kind = K_IDLE; need = false;
-            } else {
-                const int *is = p.istate + (size_t)idx * FGD_ISTATE;
-                const int status = is[FGD_I_STATUS];
-                if (status != FGD_ST_DONE) {            // DONE: finished in an earlier launch, take the next one
-                    const float *fs = p.fstate + (size_t)idx * FGD_FSTATE;
-                    st.traj = (int)idx;
-                    st.done_iters = 0; st.j = 0; st.alpha_norm = 0.0f;
-                    if (status == FGD_ST_FRESH) {
-                        st.lam_sg = p.lam_sg0; st.lam_jl = p.lam_jl0;
-                        st.lr = (p.mode == 0) ? p.bls_lr0 : p.gd_lr[0];
-                        st.outer = 0; st.inner = 0; st.inner_total = 0; st.cand_evals = 0; st.accepts = 0; st.ful = 0; st.hash = 0u;
-                        st.loss = 0.0f; st.toc = 0.0f; st.last_new = 0.0f;
-                    } else {
-                        st.lam_sg = fs[FGD_F_LAM_SG]; st.lam_jl = fs[FGD_F_LAM_JL]; st.lr = fs[FGD_F_LR];
-                        st.loss = fs[FGD_F_LOSS]; st.toc = fs[FGD_F_TOC]; st.last_new = fs[FGD_F_LAST_NEW_LOSS];
-                        st.outer = is[FGD_I_OUTER]; st.inner = is[FGD_I_INNER]; st.inner_total = is[FGD_I_INNER_TOTAL];
-                        st.cand_evals = is[FGD_I_CAND_EVALS]; st.accepts = is[FGD_I_ACCEPTS]; st.ful = is[FGD_I_FULFILLED];
-                        st.hash = (unsigned)is[FGD_I_HASH];
-                    }
-#pragma unroll
-                    for (int b = 0; b < 3; ++b) { st.start[b] = p.start[(size_t)idx * 3 + b]; st.goal[b] = p.goal[(size_t)idx * 3 + b]; }
-                    const float *ap = p.alpha + (size_t)idx * p.T * 3;
-#pragma unroll
-                    for (int pr = 0; pr < R / 2; ++pr) {
-                        const int t = G.gl * R + 2 * pr;
-                        const bool ok = t < p.T, ok1 = t + 1 < p.T;
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) a[pr][c] = mk2(ok ? ap[t * 3 + c] : 0.0f, ok1 ? ap[t * 3 + 3 + c] : 0.0f);
-                    }
-                    kind = K_EVAL0;
-                    need = false;
-                }
-            }
+        if constexpr (WPT == 1) {
+            if (G.lane == 0) idx = atomicAdd(p.queue, 1u);
+            idx = __shfl_sync(FULL, idx, 0);
+        } else {
+            unsigned *xf = reinterpret_cast<unsigned *>(G.xch + XCH_FETCH);
+            G.sync();                                 // the previous round's readers are done
+            if (G.tl == 0) *xf = atomicAdd(p.queue, 1u);
+            G.sync();
+            idx = *xf;
         }
+        if (idx >= (unsigned)p.B) { st.traj = -1; kind = K_IDLE; return; }
+        const int *is = p.istate + (size_t)idx * FGD_ISTATE;
+        const int status = is[FGD_I_STATUS];
+        if (status == FGD_ST_DONE) continue;          // finished in an earlier launch, take the next one
+        const float *fs = p.fstate + (size_t)idx * FGD_FSTATE;
+        st.traj = (int)idx;
+        st.done_iters = 0; st.j = 0; st.alpha_norm = 0.0f;
+        if (status == FGD_ST_FRESH) {
+            st.lam_sg = p.lam_sg0; st.lam_jl = p.lam_jl0;
+            st.lr = (p.mode == 0) ? p.bls_lr0 : p.gd_lr[0];
+            st.outer = 0; st.inner = 0; st.inner_total = 0; st.cand_evals = 0; st.accepts = 0; st.ful = 0; st.hash = 0u;
+            st.loss = 0.0f; st.toc = 0.0f; st.last_new = 0.0f;
+        } else {
+            st.lam_sg = fs[FGD_F_LAM_SG]; st.lam_jl = fs[FGD_F_LAM_JL]; st.lr = fs[FGD_F_LR];
+            st.loss = fs[FGD_F_LOSS]; st.toc = fs[FGD_F_TOC]; st.last_new = fs[FGD_F_LAST_NEW_LOSS];
+            st.outer = is[FGD_I_OUTER]; st.inner = is[FGD_I_INNER]; st.inner_total = is[FGD_I_INNER_TOTAL];
+            st.cand_evals = is[FGD_I_CAND_EVALS]; st.accepts = is[FGD_I_ACCEPTS]; st.ful = is[FGD_I_FULFILLED];
+            st.hash = (unsigned)is[FGD_I_HASH];
+        }
+#pragma unroll
+        for (int b = 0; b < 3; ++b) { st.start[b] = p.start[(size_t)idx * 3 + b]; st.goal[b] = p.goal[(size_t)idx * 3 + b]; }
+        const float *ap = p.alpha + (size_t)idx * p.T * 3;
+        const int t = G.tl * R;
+        const bool ok = t < p.T, ok1 = t + 1 < p.T;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) a[c] = mk2(ok ? ap[t * 3 + c] : 0.0f, ok1 ? ap[t * 3 + 3 + c] : 0.0f);
+        kind = K_EVAL0;
+        return;
     }
-    __syncwarp();
 }
 
 template <bool KS>
@@ -205,153 +149,130 @@ __device__ __forceinline__ void stage_constants(const DevParams &p, const SmemLa
 }
 
 // ---------------------------------------------------------------------------
-// Persistent optimiser: every group of LPT lanes runs one trajectory as an
+// Persistent optimiser: every team of WPT warps runs one trajectory as an
 // autonomous state machine and keeps pulling trajectories until the batch queue
-// is empty.  One loop trip = one contraction (K loads shared by the groups of
-// the warp) + the group's post-processing (candidate evaluation or gradient).
+// is empty.  One loop trip = one contraction + the post-processing of its result
+// (candidate evaluation or gradient).  NW warps per CTA; WPT > 1 requires
+// NW == WPT (the CTA barrier is the team barrier).
 // ---------------------------------------------------------------------------
-template <int LPT, int R, bool STRICT, bool KS, int NW, int MINB, bool LEAN>
+template <int WPT, bool STRICT, bool KS, int NW, int MINB>
 __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __grid_constant__ DevParams p)
 {
-    static_assert(!LEAN || LPT == 32, "LEAN variants are one warp per trajectory");
+    static_assert(WPT == 1 || NW == WPT, "multi-warp teams own their CTA");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int GPW = 32 / LPT;                    // groups (trajectories) per warp
+    constexpr int TEAMS = NW / WPT;
     const int T = p.T;
-    const SmemLayout L = make_layout(T, LPT * R, p.n_obs, KS, NW * GPW, LEAN);
+    const SmemLayout L = make_layout(T, WPT * 32 * R, p.n_obs, KS, TEAMS, WPT);
     float *sKD = reinterpret_cast<float *>(smem_raw);
     float *sKO = sKD + 2 * L.k_floats;
     float2 *sObs = reinterpret_cast<float2 *>(sKO + L.k_floats);
-    float4 *sX = reinterpret_cast<float4 *>(sObs + L.obs_pairs);
+    unsigned char *sTeams = reinterpret_cast<unsigned char *>(sObs + L.obs_pairs);
     stage_constants<KS>(p, L, sKD, sKO, sObs, NW * 32);
 
-    const Group<LPT> G;
-    const int warp = threadIdx.x >> 5;
-    const int gidx = warp * GPW + (G.lane / LPT);
-    const float *kd = (KS ? sKD : p.KD) + G.gl * 2 * R;
-    const float *ko = (KS ? sKO : p.KO) + G.gl * R;
-    float4 *XA = sX + (size_t)(gidx * 2) * (L.x_rows + L.ad_rows), *XB = XA + L.x_rows;
-    float4 *SA = XB + L.x_rows, *SD = SA + L.ad_rows;      // LEAN: alpha / direction rows, lane-major
+    const int team = (threadIdx.x >> 5) / WPT;
+    float4 *XA = reinterpret_cast<float4 *>(sTeams + (size_t)team * L.team_bytes()), *XB = XA + L.x_rows;
+    const Team<WPT> G(reinterpret_cast<float *>(XB + L.x_rows));
+    const float *kd = (KS ? sKD : p.KD) + G.tl * 2 * R;
+    const float *ko = (KS ? sKO : p.KO) + G.tl * R;
 
     int kind = K_IDLE;
-    Slot st;                   // warp-uniform loop state of this warp's trajectory (registers)
+    Slot st;                   // team-uniform loop state of this team's trajectory (registers)
     st.traj = -1;
-    unsigned nz[R];            // non-zero rows of the velocity gradient operand (see contract_back)
+    unsigned nz[WPT][R];       // non-zero rows of the velocity gradient operand (see contract_back)
 #pragma unroll
-    for (int r = 0; r < R; ++r) nz[r] = 0u;
-    constexpr int RP = R / 2;
-    f2 a[RP][3];       // alpha rows of this lane, as row pairs (.x = row 2p, .y = row 2p+1)
-    f2 d[RP][3];       // step direction rows (normalised gradient for BLS, gradient for GD)
+    for (int w = 0; w < WPT; ++w) { nz[w][0] = 0u; nz[w][1] = 0u; }
+    f2 a[3], d[3];             // alpha rows and step direction rows (normalised gradient for BLS, gradient for GD)
 #pragma unroll
-    for (int pr = 0; pr < RP; ++pr)
-#pragma unroll
-        for (int b = 0; b < 3; ++b) { a[pr][b] = bc2(0.0f); d[pr][b] = bc2(0.0f); }
-    bool boot = true;          // first trip: nothing to contract yet, just fill the slots through the common tail
+    for (int b = 0; b < 3; ++b) { a[b] = bc2(0.0f); d[b] = bc2(0.0f); }
+    bool boot = true;          // first trip: nothing to contract yet, just fill the slot through the common tail
     for (;;) {
-        f2 y1[RP][3], y2[RP][3];
+        f2 y1[3], y2[3];
         if (!boot) {
-            if (!__any_sync(FULL, kind != K_IDLE)) break;
-            __syncwarp();
-            if (kind != K_BACK) contract<LPT, R, KS, true>(kd, T, XA, XA, y1, y2);       // forward: K x, dK x
-            else contract_back<LPT, R, KS>(ko, kd, T, XA, XB, nz, y1, y2);               // backward: K G_q + dK (-G_v)
-            __syncwarp();
+            if (kind == K_IDLE) break;
+            G.sync();                                                                    // operands complete
+            if (kind != K_BACK) contract<WPT, KS, true>(kd, T, XA, XA, y1, y2);          // forward: K x, dK x
+            else { load_nz<WPT>(G, nz); contract_back<WPT, KS>(ko, kd, T, XA, XB, nz, y1, y2); }   // backward: K G_q + dK (-G_v)
+            G.sync();                                                                    // operands consumed
         }
         TRACE("lane %d trip boot=%d kind=%d\n", threadIdx.x, (int)boot, kind);
-        const bool is_back = !boot && kind == K_BACK;
-        const bool is_fwd = !boot && (kind == K_EVAL0 || kind == K_CAND);
         bool want_cand = false;     // write the next candidate into XA
         bool want_head = false;     // go to the head of the inner loop
         bool want_end = false;      // inner loop finished: constraint check / lambda escalation
         bool want_eval = false;     // (re-)evaluate loss and gradient operands at alpha
 
-        __syncwarp();
-        if (__any_sync(FULL, is_back)) {
+        if (!boot && kind == K_BACK) {
             // ---- alpha-gradient, normalisation, first candidate ------------------------------
-            f2 g[RP][3];
-            backward_rows<R>(p, y1, y2, g);
-            float alpha_norm = 0.0f, scale = 1.0f;
+            f2 g[3];
+            backward_rows(p, y1, y2, g);
+            float alpha_norm = 0.0f;
             if (p.mode == 0) {
+                const bool v0 = G.tl * R < T, v1 = G.tl * R + 1 < T;
                 float part = 0.0f;
-#pragma unroll
-                for (int pr = 0; pr < RP; ++pr) {
-                    const f2 ss = ss3_2(g[pr][0], g[pr][1], g[pr][2]);
-                    if (G.gl * R + 2 * pr < T) part = part + ss.x;
-                    if (G.gl * R + 2 * pr + 1 < T) part = part + ss.y;
-                }
-                scale = 1.0f / sqrtf(gsum<LPT>(part));                                 // optimizer_BLS.py:165
+                const f2 ss = ss3_2(g[0], g[1], g[2]);
+                if (v0) part = part + ss.x;
+                if (v1) part = part + ss.y;
+                const float scale = 1.0f / sqrtf(tsum<WPT>(G, part, XCH_NORM));          // optimizer_BLS.py:165
                 float pb = 0.0f;
-#pragma unroll
-                for (int pr = 0; pr < RP; ++pr) {
-                    const f2 n0 = mul2(g[pr][0], bc2(scale)), n1 = mul2(g[pr][1], bc2(scale)), n2 = mul2(g[pr][2], bc2(scale));
-                    const f2 pp = mul2(add2(add2(g[pr][0], g[pr][1]), g[pr][2]), add2(add2(n0, n1), n2));
-                    if (G.gl * R + 2 * pr < T) pb = pb + pp.x;
-                    if (G.gl * R + 2 * pr + 1 < T) pb = pb + pp.y;
-                    g[pr][0] = n0; g[pr][1] = n1; g[pr][2] = n2;
-                }
-                alpha_norm = gsum<LPT>(pb);                                            // optimizer_BLS.py:166
+                const f2 n0 = mul2(g[0], bc2(scale)), n1 = mul2(g[1], bc2(scale)), n2 = mul2(g[2], bc2(scale));
+                const f2 pp = mul2(add2(add2(g[0], g[1]), g[2]), add2(add2(n0, n1), n2));
+                if (v0) pb = pb + pp.x;
+                if (v1) pb = pb + pp.y;
+                g[0] = n0; g[1] = n1; g[2] = n2;
+                alpha_norm = tsum<WPT>(G, pb, XCH_ANORM);                                // optimizer_BLS.py:166
             }
-            if (is_back) {
 #pragma unroll
-                for (int pr = 0; pr < RP; ++pr)
-#pragma unroll
-                    for (int b = 0; b < 3; ++b) d[pr][b] = g[pr][b];
-                if constexpr (LEAN) st_rows<R>(SD, G.lane, d);
-                st.alpha_norm = alpha_norm; st.j = 0;
-                want_cand = true;
-                kind = K_CAND;
-            }
-        }
-        __syncwarp();
-        if (__any_sync(FULL, is_fwd)) {
+            for (int b = 0; b < 3; ++b) d[b] = g[b];
+            st.alpha_norm = alpha_norm; st.j = 0;
+            want_cand = true;
+            kind = K_CAND;
+        } else if (!boot) {
             // ---- loss (and, if accepted, gradient operands) at alpha or at a candidate -------
-            Rows<R, LEAN> Rw;
+            Rows Rw;
             float loss_c, toc_c;
             int ful_c;
-            cost_phase<LPT, R, STRICT, LEAN>(p, sObs, G, y1, y2, st.start, st.goal, st.lam_sg, st.lam_jl, Rw, loss_c, toc_c, ful_c);
+            cost_phase<WPT, STRICT>(p, sObs, G, y1, y2, st.start, st.goal, st.lam_sg, st.lam_jl, Rw, loss_c, toc_c, ful_c);
             bool accept = false;
-            if (is_fwd) {
-                if (kind == K_EVAL0) {
-                    st.loss = loss_c; st.toc = toc_c; st.ful = ful_c;
-                    accept = true; want_head = true;
+            if (kind == K_EVAL0) {
+                st.loss = loss_c; st.toc = toc_c; st.ful = ful_c;
+                accept = true; want_head = true;
+            } else {
+                st.cand_evals += 1;
+                const float lr = st.lr, loss = st.loss;
+                const bool minimized = (loss - loss_c < p.eps_loop);               // optimizer_BLS.py:178, optimizer_GD.py:194
+                bool rejected = false;
+                if (p.mode == 0) {                                                 // Armijo test, optimizer_BLS.py:141-149
+                    const float req = loss - (p.bls_alpha * lr) * st.alpha_norm;
+                    rejected = loss_c > req;
                 } else {
-                    st.cand_evals += 1;
-                    const float lr = st.lr, loss = st.loss;
-                    const bool minimized = (loss - loss_c < p.eps_loop);               // optimizer_BLS.py:178, optimizer_GD.py:194
-                    bool rejected = false;
-                    if (p.mode == 0) {                                                 // Armijo test, optimizer_BLS.py:141-149
-                        const float req = loss - (p.bls_alpha * lr) * st.alpha_norm;
-                        rejected = loss_c > req;
+                    st.last_new = loss_c;
+                }
+                if (rejected) {
+                    st.lr = lr * p.bls_bm; hash_step(st, 1u);
+                    st.j += 1;
+                    if (st.j < p.max_bls) {
+                        want_cand = true;
                     } else {
-                        st.last_new = loss_c;
+                        // every candidate rejected: new_loss := loss (optimizer_BLS.py:170,178)
+                        st.last_new = loss;
+                        if (loss - loss < p.eps_loop) { hash_step(st, 3u); want_end = true; }
+                        else { st.inner += 1; want_eval = true; }
                     }
-                    if (rejected) {
-                        st.lr = lr * p.bls_bm; hash_step(st, 1u);
-                        st.j += 1;
-                        if (st.j < p.max_bls) {
-                            want_cand = true;
-                        } else {
-                            // every candidate rejected: new_loss := loss (optimizer_BLS.py:170,178)
-                            st.last_new = loss;
-                            if (loss - loss < p.eps_loop) { hash_step(st, 3u); want_end = true; }
-                            else { st.inner += 1; want_eval = true; }
-                        }
-                    } else if (p.mode == 1 && minimized) {
-                        hash_step(st, 3u); want_end = true;    // GD: the candidate is discarded (optimizer_GD.py:191-192)
-                    } else {
-                        if constexpr (LEAN) { ld_rows<R>(SA, G.lane, a); ld_rows<R>(SD, G.lane, d); }
-                        accept_candidate<R>(p, lr, a, d);
-                        if constexpr (LEAN) st_rows<R>(SA, G.lane, a);
-                        accept = true;
-                        if (p.mode == 0) st.lr = lr * p.bls_bp;
-                        st.accepts += 1; hash_step(st, 2u);
-                        st.ful = ful_c; st.toc = toc_c; st.last_new = loss_c; st.loss = loss_c;
-                        if (minimized) { hash_step(st, 3u); want_end = true; }       // BLS keeps the accepted alpha
-                        else { st.inner += 1; want_head = true; }
-                    }
+                } else if (p.mode == 1 && minimized) {
+                    hash_step(st, 3u); want_end = true;    // GD: the candidate is discarded (optimizer_GD.py:191-192)
+                } else {
+                    f2 c[3];
+                    make_candidate(p, lr, a, d, c);
+#pragma unroll
+                    for (int b = 0; b < 3; ++b) a[b] = c[b];
+                    accept = true;
+                    if (p.mode == 0) st.lr = lr * p.bls_bp;
+                    st.accepts += 1; hash_step(st, 2u);
+                    st.ful = ful_c; st.toc = toc_c; st.last_new = loss_c; st.loss = loss_c;
+                    if (minimized) { hash_step(st, 3u); want_end = true; }       // BLS keeps the accepted alpha
+                    else { st.inner += 1; want_head = true; }
                 }
             }
-            __syncwarp();
-            if (__any_sync(FULL, accept))
-                grad_phase<LPT, R, LEAN>(p, G, Rw, y1, y2, st.start, st.goal, st.lam_sg, st.lam_jl, XA, XB, accept, nz);
+            if (accept) grad_phase<WPT>(p, G, Rw, st.start, st.goal, st.lam_sg, st.lam_jl, XA, XB, nz);
         }
         // ---- common tail: loop heads, retirement, refill -------------------------------------
         bool save_active = false;
@@ -378,28 +299,21 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
                 want_eval = true;
             }
         }
-        const bool refill = retire || save_active || boot;
-        TRACE("lane %d tail head=%d end=%d refill=%d kind=%d\n", threadIdx.x, (int)want_head, (int)want_end, (int)refill, kind);
-        __syncwarp();
-        if (__any_sync(FULL, refill)) {
-            if (refill && !boot) {
-                if constexpr (LEAN) ld_rows<R>(SA, G.lane, a);
-                save_slot<LPT, R>(p, G, st, retire ? FGD_ST_DONE : FGD_ST_ACTIVE, a);
-            }
-            fetch_slot<LPT, R>(p, G, refill, st, kind, a);
-            if (refill) {
-                want_eval = (kind != K_IDLE);
-                if constexpr (LEAN) st_rows<R>(SA, G.lane, a);
-            }
+        if (retire || save_active || boot) {
+            if (!boot) save_slot<WPT>(p, G, st, retire ? FGD_ST_DONE : FGD_ST_ACTIVE, a);
+            fetch_slot<WPT>(p, G, st, kind, a);
+            want_eval = (kind != K_IDLE);
         }
-        TRACE("lane %d after fetch kind=%d traj=%d\n", threadIdx.x, kind, st.traj);
         if (want_eval) {
-            if constexpr (LEAN) ld_rows<R>(SA, G.lane, a);
-            begin_outer_eval<LPT, R>(p, G, st, kind, a, XA);
+            // (re)start with the loss and gradient operands at the current alpha: optimizer_BLS.py:163, optimizer_GD.py:210
+            if (p.mode == 1) st.lr = p.gd_lr[st.outer];
+            write_rows<WPT>(p, G, a, XA);
+            kind = K_EVAL0;
         }
         if (want_cand) {
-            if constexpr (LEAN) { ld_rows<R>(SA, G.lane, a); ld_rows<R>(SD, G.lane, d); }
-            write_candidate<LPT, R>(p, G, st.lr, a, d, XA);
+            f2 c[3];
+            make_candidate(p, st.lr, a, d, c);
+            write_rows<WPT>(p, G, c, XA);
         }
         boot = false;
     }
@@ -407,111 +321,76 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
 
 // ---------------------------------------------------------------------------
 // Evaluation only (unit-parity hook and the host's compute_trajectory_cost*):
-// one group per trajectory, grid-stride.
+// one team per trajectory, grid-stride.
 // ---------------------------------------------------------------------------
-template <int LPT, int R, bool STRICT, bool KS, int NW>
+template <int WPT, bool STRICT, bool KS, int NW>
 __global__ void __launch_bounds__(NW * 32) fgd_eval_kernel(const __grid_constant__ DevParams p, const EvalPtrs e)
 {
+    static_assert(WPT == 1 || NW == WPT, "multi-warp teams own their CTA");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int GPW = 32 / LPT;
+    constexpr int TEAMS = NW / WPT;
     const int T = p.T;
-    const SmemLayout L = make_layout(T, LPT * R, p.n_obs, KS, NW * GPW, false);
+    const SmemLayout L = make_layout(T, WPT * 32 * R, p.n_obs, KS, TEAMS, WPT);
     float *sKD = reinterpret_cast<float *>(smem_raw);
     float *sKO = sKD + 2 * L.k_floats;
     float2 *sObs = reinterpret_cast<float2 *>(sKO + L.k_floats);
-    float4 *sX = reinterpret_cast<float4 *>(sObs + L.obs_pairs);
-    MARK(1);
+    unsigned char *sTeams = reinterpret_cast<unsigned char *>(sObs + L.obs_pairs);
     stage_constants<KS>(p, L, sKD, sKO, sObs, NW * 32);
-    MARK(2);
 
-    const Group<LPT> G;
-    const int warp = threadIdx.x >> 5;
-    const int gidx = warp * GPW + (G.lane / LPT);
-    const float *kd = (KS ? sKD : p.KD) + G.gl * 2 * R;
-    float4 *XA = sX + (size_t)(gidx * 2) * L.x_rows, *XB = XA + L.x_rows;
-    const int stride = gridDim.x * NW * GPW;
-    const int n_rounds = (p.B + stride - 1) / stride;
+    const int team = (threadIdx.x >> 5) / WPT;
+    float4 *XA = reinterpret_cast<float4 *>(sTeams + (size_t)team * L.team_bytes()), *XB = XA + L.x_rows;
+    const Team<WPT> G(reinterpret_cast<float *>(XB + L.x_rows));
+    const float *kd = (KS ? sKD : p.KD) + G.tl * 2 * R;
+    const int stride = gridDim.x * TEAMS;
+    const int t0 = G.tl * R;
 
-    // operand buffers start defined (dead groups contract whatever is there and write nothing)
+    for (int b = blockIdx.x * TEAMS + team; b < p.B; b += stride) {       // team-uniform trip count
+        float start[3], goal[3];
+        const float *ap = p.alpha + (size_t)b * T * 3;
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const int t = G.gl * R + r;
-        if (t < T) { XA[t] = make_float4(0.f, 0.f, 0.f, 0.f); XB[t] = make_float4(0.f, 0.f, 0.f, 0.f); }
-    }
-
-    for (int round = 0; round < n_rounds; ++round) {
-        const int b = round * stride + blockIdx.x * NW * GPW + gidx;
-        const bool live = b < p.B;
-        float start[3] = {0.f, 0.f, 0.f}, goal[3] = {0.f, 0.f, 0.f};
-        if (live) {
-            const float *ap = p.alpha + (size_t)b * T * 3;
+        for (int r = 0; r < R; ++r)
+            if (t0 + r < T) XA[t0 + r] = make_float4(ap[(t0 + r) * 3], ap[(t0 + r) * 3 + 1], ap[(t0 + r) * 3 + 2], 0.0f);
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const int t = G.gl * R + r;
-                if (t < T) XA[t] = make_float4(ap[t * 3], ap[t * 3 + 1], ap[t * 3 + 2], 0.0f);
-            }
-#pragma unroll
-            for (int k = 0; k < 3; ++k) { start[k] = p.start[(size_t)b * 3 + k]; goal[k] = p.goal[(size_t)b * 3 + k]; }
+        for (int k = 0; k < 3; ++k) { start[k] = p.start[(size_t)b * 3 + k]; goal[k] = p.goal[(size_t)b * 3 + k]; }
+        f2 y1[3], y2[3];
+        G.sync();
+        contract<WPT, KS, true>(kd, T, XA, XA, y1, y2);
+        G.sync();
+        Rows Rw;
+        float loss, toc;
+        int ful;
+        cost_phase<WPT, STRICT>(p, sObs, G, y1, y2, start, goal, e.lam_sg, e.lam_jl, Rw, loss, toc, ful);
+        if (G.tl == 0) {
+            if (e.loss) e.loss[b] = loss;
+            if (e.toc) e.toc[b] = toc;
+            if (e.fulfilled) e.fulfilled[b] = ful;
         }
-        f2 y1[R / 2][3], y2[R / 2][3];
-        MARK(3);
-        __syncwarp();
-        contract<LPT, R, KS, true>(kd, T, XA, XA, y1, y2);
-        MARK(4);
-        __syncwarp();
-        {
-            constexpr bool LEAN = (R > 2);
-            Rows<R, LEAN> Rw;
-            float loss, toc;
-            int ful;
-            cost_phase<LPT, R, STRICT, LEAN>(p, sObs, G, y1, y2, start, goal, e.lam_sg, e.lam_jl, Rw, loss, toc, ful);
-            MARK(5);
-            if (live && G.gl == 0) {
-                if (e.loss) e.loss[b] = loss;
-                if (e.toc) e.toc[b] = toc;
-                if (e.fulfilled) e.fulfilled[b] = ful;
-            }
 #pragma unroll
-            for (int pr = 0; pr < R / 2; ++pr) {
-                const int t = G.gl * R + 2 * pr;
-                if (live && t < T && (e.q || e.v)) {
-                    f2 q[3], v[3], sn[3], cs[3];
-                    row_kinematics(p, y1[pr], y2[pr], q, v, sn, cs);
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-                        if (e.q) e.q[((size_t)b * T + t) * 3 + k] = q[k].x;
-                        if (e.v) e.v[((size_t)b * T + t) * 3 + k] = v[k].x;
-                        if (t + 1 < T) {
-                            if (e.q) e.q[((size_t)b * T + t + 1) * 3 + k] = q[k].y;
-                            if (e.v) e.v[((size_t)b * T + t + 1) * 3 + k] = v[k].y;
-                        }
-                    }
-                }
+        for (int k = 0; k < 3; ++k) {
+            if (t0 < T) {
+                if (e.q) e.q[((size_t)b * T + t0) * 3 + k] = Rw.q[k].x;
+                if (e.v) e.v[((size_t)b * T + t0) * 3 + k] = Rw.v[k].x;
             }
-            unsigned nz_unused[R];
-            if (e.grad) grad_phase<LPT, R, LEAN>(p, G, Rw, y1, y2, start, goal, e.lam_sg, e.lam_jl, XA, XB, live, nz_unused);
+            if (t0 + 1 < T) {
+                if (e.q) e.q[((size_t)b * T + t0 + 1) * 3 + k] = Rw.q[k].y;
+                if (e.v) e.v[((size_t)b * T + t0 + 1) * 3 + k] = Rw.v[k].y;
+            }
         }
         if (e.grad) {
-            __syncwarp();
-            contract<LPT, R, KS, false>(kd, T, XA, XB, y1, y2);
-            if (live) {
-                f2 g[R / 2][3];
-                backward_rows<R>(p, y1, y2, g);
+            unsigned nz_unused[WPT][R];
+            grad_phase<WPT>(p, G, Rw, start, goal, e.lam_sg, e.lam_jl, XA, XB, nz_unused);
+            G.sync();
+            contract<WPT, KS, false>(kd, T, XA, XB, y1, y2);      // dense reference form of the backward contraction
+            f2 g[3];
+            backward_rows(p, y1, y2, g);
 #pragma unroll
-                for (int pr = 0; pr < R / 2; ++pr) {
-                    const int t = G.gl * R + 2 * pr;
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-                        if (t < T) e.grad[((size_t)b * T + t) * 3 + k] = g[pr][k].x;
-                        if (t + 1 < T) e.grad[((size_t)b * T + t + 1) * 3 + k] = g[pr][k].y;
-                    }
-                }
+            for (int k = 0; k < 3; ++k) {
+                if (t0 < T) e.grad[((size_t)b * T + t0) * 3 + k] = g[k].x;
+                if (t0 + 1 < T) e.grad[((size_t)b * T + t0 + 1) * 3 + k] = g[k].y;
             }
         }
-        MARK(6);
-        __syncwarp();
+        G.sync();
     }
-    MARK(7);
 }
 
 // ---------------------------------------------------------------------------

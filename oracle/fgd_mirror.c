@@ -111,33 +111,34 @@ static void mirror_sincos(float x, float *s_out, float *c_out)
 }
 
 /* ---- fixed-order reductions -------------------------------------------- */
-/* A trajectory is owned by LPT lanes; lane l owns the R adjacent rows t = R*l .. R*l+R-1
- * (LPT*R >= T).  Sum over t: lane partial = sequential sum over its rows (from +0), then an
- * xor butterfly LPT/2, ..., 2, 1 over the lanes.  Same mapping table as the CUDA side.   */
-static void mapping_for(int T, int *LPT, int *R)
-{
-    *LPT = 32;                      /* one warp per trajectory */
-    if (T <= 64) *R = 2;
-    else if (T <= 128) *R = 4;
-    else *R = 8;
-}
+/* A trajectory is owned by a team of WPT warps (1, 2 or 4 for T <= 64, 128, 256); team thread i
+ * owns the 2 adjacent rows t = 2i, 2i+1.  Sum over t: thread partial = sequential sum over its
+ * rows (from +0), then an xor butterfly 16, 8, 4, 2, 1 inside each warp, then the warp partials
+ * are combined as p0 + p1 (WPT = 2) or (p0 + p1) + (p2 + p3) (WPT = 4).  Same mapping as the
+ * CUDA side (csrc/fgd_device.cuh).                                                         */
+static int warps_per_trajectory(int T) { return T <= 64 ? 1 : (T <= 128 ? 2 : (T <= 256 ? 4 : 8)); }
 
 static float tree_sum(const float *x, int T)
 {
-    int LPT, R;
-    mapping_for(T, &LPT, &R);
-    float p[32];
-    for (int l = 0; l < LPT; ++l) {
-        float a = 0.0f;
-        for (int r = 0; r < R; ++r) { const int t = R * l + r; if (t < T) a = a + x[t]; }
-        p[l] = a;
+    const int WPT = warps_per_trajectory(T);
+    float wp[8];
+    for (int w = 0; w < WPT; ++w) {
+        float p[32];
+        for (int l = 0; l < 32; ++l) {
+            float a = 0.0f;
+            for (int r = 0; r < 2; ++r) { const int t = 2 * (32 * w + l) + r; if (t < T) a = a + x[t]; }
+            p[l] = a;
+        }
+        for (int off = 16; off >= 1; off >>= 1) {
+            float q[32];
+            for (int l = 0; l < 32; ++l) q[l] = p[l] + p[l ^ off];
+            memcpy(p, q, sizeof(p));
+        }
+        wp[w] = p[0];
     }
-    for (int off = LPT / 2; off >= 1; off >>= 1) {
-        float q[32];
-        for (int l = 0; l < LPT; ++l) q[l] = p[l] + p[l ^ off];
-        memcpy(p, q, sizeof(float) * LPT);
-    }
-    return p[0];
+    for (int n = WPT; n > 1; n >>= 1)
+        for (int w = 0; w < n / 2; ++w) wp[w] = wp[2 * w] + wp[2 * w + 1];
+    return wp[0];
 }
 
 static inline float ss3(float a, float b, float c) { return fmaf(c, c, fmaf(b, b, a * a)); }

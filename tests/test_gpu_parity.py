@@ -102,7 +102,7 @@ def test_eval_lambda_max_override(cuda_ready):
         assert np.array_equal(g["loss"], c["loss"])
 
 
-@pytest.mark.parametrize("mode,gpw,T,n_obs,B,over", [
+@pytest.mark.parametrize("mode,wpt,T,n_obs,B,over", [
     ("bls", 1, 50, 11, 200, {}),
     ("bls", 1, 50, 11, 333, {}),
     ("bls", 1, 64, 11, 61, {}),
@@ -111,11 +111,11 @@ def test_eval_lambda_max_override(cuda_ready):
     ("bls", 1, 24, 30, 100, {}),
     ("bls", 1, 7, 3, 37, {}),
     ("bls", 1, 33, 11, 24, {}),
-    ("bls", 1, 100, 40, 48, {"max_inner_iteration": 40, "max_outer_iteration": 3}),
-    ("bls", 1, 256, 200, 16, {"max_inner_iteration": 12, "max_outer_iteration": 2}),
+    ("bls", 2, 100, 40, 48, {"max_inner_iteration": 40, "max_outer_iteration": 3}),
+    ("bls", 4, 256, 200, 16, {"max_inner_iteration": 12, "max_outer_iteration": 2}),
     ("bls", 1, 50, 11, 64, {"constraint_violating_dependant_loss": False, "lambda_max_cost": 0.25}),
 ])
-def test_optimize_bit_exact_strict(cuda_ready, mode, gpw, T, n_obs, B, over):
+def test_optimize_bit_exact_strict(cuda_ready, mode, wpt, T, n_obs, B, over):
     """Whole optimisation (all outer / inner / line-search iterations) bit-identical to the oracle:
     final alpha, penalty weights, step size, loss, counters and decision hash of every trajectory."""
     args, tr, obs, start, goal, alpha0 = _setup(T=T, n_obs=n_obs, B=B, seed=B, **over)
@@ -127,7 +127,7 @@ def test_optimize_bit_exact_strict(cuda_ready, mode, gpw, T, n_obs, B, over):
     assert len(bad) == 0, (len(bad), bad[:5], is_g[bad[:3]], cis[bad[:3]])
     assert np.array_equal(a.cpu().numpy(), ca)
     assert np.array_equal(fs_g[:, :6], cfs[:, :6])
-    assert tr.handle.launch_geometry(B)["trajectories_per_warp"] == gpw
+    assert tr.handle.launch_geometry(B)["warps_per_trajectory"] == wpt
 
 
 def test_budgeted_launches_and_resume_bit_exact(cuda_ready):

@@ -319,8 +319,9 @@ __device__ __forceinline__ void row_kinematics(const DevParams &p, const f2 (&yq
     sincos_cw2(c3, sn[2], cs[2]);
 }
 
-// U obstacles against the row pair (environment.py:32-58): sr += 1/den, sx += dx/den^2, sy += dy/den^2
-// with den = 0.5 + 0.5 |f - o|^2.  Three stages (distances -> reciprocals -> accumulation) so that U
+// U obstacles against the row pair (environment.py:32-58) in the scaled form m = 2 den = 1 + |f - o|^2:
+// sr += 1/m, sx += dx/m^2, sy += dy/m^2; the powers of two are exact and folded into the per-sample
+// constants (0.8 * 2, -0.8 * 4), which saves one FP32 operation per (sample, obstacle) pair.  Three stages (distances -> reciprocals -> accumulation) so that U
 // independent packed chains are in flight across the MUFU latency; the accumulation stage visits the
 // obstacles in ascending order (the oracle's summation order).
 template <int U, bool STRICT>
@@ -341,8 +342,7 @@ __device__ __forceinline__ void obstacle_block(const float2 *__restrict__ obs, c
     for (int u = 0; u < U; ++u) {
         dx[u] = add2(x, bc2(-ob[u].x));
         dy[u] = add2(y, bc2(-ob[u].y));
-        const f2 n = fma2(dy[u], dy[u], mul2(dx[u], dx[u]));
-        rr[u] = fma2(bc2(0.5f), n, bc2(0.5f));
+        rr[u] = fma2(dy[u], dy[u], fma2(dx[u], dx[u], bc2(1.0f)));
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) rr[u] = mk2(rcp<STRICT>(rr[u].x), rcp<STRICT>(rr[u].y));
@@ -361,8 +361,8 @@ __device__ __forceinline__ void obstacle_block(const float2 *__restrict__ obs, c
 //   trajectory.py:271-281 (total), :81-88 (max/mean), :183-255 (penalties),
 //   :129-137 + robot.py:90-113 (constraint predicates), robot.py:29-36 (fk),
 //   environment.py:32-58 (obstacle potential and its (x,y)-gradient).
-// The obstacle loop accumulates sum 1/den and sum d/den^2; the constant factors
-// 0.8 and -0.8 of environment.py:43,57 are applied once per sample.
+// The obstacle loop accumulates sum 1/(2 den) and sum d/(2 den)^2; the constant factors
+// 0.8 and -0.8 of environment.py:43,57 (times 2 and 4) are applied once per sample.
 // ---------------------------------------------------------------------------
 template <int WPT, bool STRICT>
 __device__ __forceinline__ void cost_phase(const DevParams &p, const float2 *__restrict__ sObs, const Team<WPT> &G,
@@ -420,8 +420,8 @@ __device__ __forceinline__ void cost_phase(const DevParams &p, const float2 *__r
     for (; o + 4 <= n_obs; o += 4) obstacle_block<4, STRICT>(sObs + o, x, y, sr, sx, sy);
     if (o + 2 <= n_obs) { obstacle_block<2, STRICT>(sObs + o, x, y, sr, sx, sy); o += 2; }
     if (o < n_obs) obstacle_block<1, STRICT>(sObs + o, x, y, sr, sx, sy);
-    const f2 cost = mul2(bc2(0.8f), sr);
-    Rw.gx = mul2(bc2(-0.8f), sx); Rw.gy = mul2(bc2(-0.8f), sy);
+    const f2 cost = mul2(bc2(1.6f), sr);
+    Rw.gx = mul2(bc2(-3.2f), sx); Rw.gy = mul2(bc2(-3.2f), sy);
     float part_c = 0.0f, lmax = 0.0f;                 // cost >= 0
     if (valid0) { part_c = part_c + cost.x; lmax = fmaxf(lmax, cost.x); }
     if (valid1) { part_c = part_c + cost.y; lmax = fmaxf(lmax, cost.y); }

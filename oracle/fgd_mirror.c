@@ -23,8 +23,9 @@
  *
  * Deliberate, documented re-associations w.r.t. the NumPy restatement (all
  * within 1-2 ulp per operation; tolerances in tests/test_oracle_mirror.py):
- *   - the obstacle term accumulates sum_o 1/den and sum_o d/den^2 (reciprocal, not
- *     division) and applies the factors 0.8 / -0.8 once per time sample
+ *   - the obstacle term works with m = 2 den = 1 + |f-o|^2 (fma(dy,dy,fma(dx,dx,1))),
+ *     accumulates sum_o 1/m and sum_o d/m^2 (reciprocal, not division) and applies
+ *     the factors 0.8*2 / -0.8*4 once per time sample (the powers of two are exact)
  *                                                  (environment.py:43,57)
  *   - (q-mean)/std, /std^2, v/vmax, /T in the limit penalties multiply by
  *     host-rounded reciprocals                     (trajectory.py:217,232,247,260)
@@ -195,15 +196,14 @@ static void evaluate_point(const MirrorCfg *c, const Derived *d, const float *K,
         float sr = 0.0f, sx = 0.0f, sy = 0.0f;
         for (int o = 0; o < c->n_obs; ++o) {                 /* environment.py:46-58 */
             float dx = x - obs[2 * o], dy = y - obs[2 * o + 1];
-            float n = fmaf(dy, dy, dx * dx);
-            float den = fmaf(0.5f, n, 0.5f);
-            float r = 1.0f / den;
-            sr = sr + r;                                     /* sum 1/den            */
+            float m = fmaf(dy, dy, fmaf(dx, dx, 1.0f));      /* 2 den = 1 + |f-o|^2  */
+            float r = 1.0f / m;
+            sr = sr + r;                                     /* sum 1/(2 den)        */
             float r2 = r * r;
-            sx = fmaf(r2, dx, sx);                           /* sum d/den^2          */
+            sx = fmaf(r2, dx, sx);                           /* sum d/(2 den)^2      */
             sy = fmaf(r2, dy, sy);
         }
-        costv[t] = 0.8f * sr; gx[t] = -0.8f * sx; gy[t] = -0.8f * sy;
+        costv[t] = 1.6f * sr; gx[t] = -3.2f * sx; gy[t] = -3.2f * sy;
         /* joint-limit penalties  trajectory.py:215-268 */
         float ep = 0.0f, ev = 0.0f;
         float e3[3], f3[3];

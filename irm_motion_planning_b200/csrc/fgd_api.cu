@@ -265,7 +265,7 @@ int fgd_create(const FgdConfig *cfg, FgdHandle **out)
         CKC(cudaMemset(h->d_obs[i], 0, (size_t)cfg->obstacle_capacity * 2 * 4));
     }
     CKC(cudaMalloc(&h->d_queue, sizeof(unsigned)));
-#ifdef FGD_DEBUG_MARK
+#if defined(FGD_DEBUG_MARK) || defined(FGD_PHASE_CLOCKS)
     CKC(cudaHostAlloc(&h->h_dbg, 4096 * sizeof(int), cudaHostAllocMapped));
     std::memset(h->h_dbg, 0, 4096 * sizeof(int));
     CKC(cudaHostGetDevicePointer(&h->d_dbg, h->h_dbg, 0));
@@ -456,7 +456,7 @@ int fgd_launch_geometry(const FgdHandle *h, int32_t B, int32_t *grid, int32_t *b
 
 int64_t fgd_kernel_launches(const FgdHandle *h) { return h ? h->launches : 0; }
 
-#ifdef FGD_DEBUG_MARK
+#if defined(FGD_DEBUG_MARK) || defined(FGD_PHASE_CLOCKS)
 int *fgd_debug_buffer(FgdHandle *h) { return h->h_dbg; }
 #endif
 

@@ -16,6 +16,12 @@
 #define MARK(id) do { } while (0)
 #endif
 
+#ifdef FGD_PHASE_CLOCKS      // debug builds: where does a lone team spend its cycles? (CTA 0, team 0 -> p.dbg)
+#define PCLK(i) do { const long long c_ = clock64(); pc[i] += c_ - pc_t; pc_t = c_; } while (0)
+#else
+#define PCLK(i) do { } while (0)
+#endif
+
 namespace fgd {
 
 // shared-memory carve-up, identical on host and device
@@ -125,25 +131,44 @@ __device__ __forceinline__ void fetch_slot(const DevParams &p, const Team<WPT> &
     }
 }
 
+// K tables -> shared memory with the TMA bulk-copy engine (cp.async.bulk, SASS UBLKCP): one thread
+// programs two copies (KD, KO) that complete on an mbarrier; every thread of the CTA then waits on the
+// barrier's phase 0.  The obstacle set (8 B granules, any count) is staged by the threads meanwhile.
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
 template <bool KS>
 __device__ __forceinline__ void stage_constants(const DevParams &p, const SmemLayout &L, float *sKD, float *sKO, float2 *sObs, int nthreads)
 {
-    // trip counts are CTA-uniform (the bound check is inside), so no warp diverges ahead of the barrier
+    __shared__ __align__(8) unsigned long long tma_bar;
     if constexpr (KS) {
-        const float4 *g4 = reinterpret_cast<const float4 *>(p.KD), *o4 = reinterpret_cast<const float4 *>(p.KO);
-        float4 *d4 = reinterpret_cast<float4 *>(sKD), *e4 = reinterpret_cast<float4 *>(sKO);
-        const int n4 = (2 * L.k_floats) / 4, m4 = L.k_floats / 4;
-#pragma unroll 1
-        for (int i0 = 0; i0 < n4; i0 += nthreads) {
-            const int i = i0 + threadIdx.x;
-            if (i < n4) d4[i] = __ldg(g4 + i);
-            if (i < m4) e4[i] = __ldg(o4 + i);
+        const unsigned bar = smem_u32(&tma_bar);
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned bytes_kd = (unsigned)(2 * L.k_floats) * 4u, bytes_ko = (unsigned)L.k_floats * 4u;     // multiples of 256 B
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes_kd + bytes_ko) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32(sKD)), "l"(p.KD), "r"(bytes_kd), "r"(bar) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32(sKO)), "l"(p.KO), "r"(bytes_ko), "r"(bar) : "memory");
         }
     }
+    // trip counts are CTA-uniform (the bound check is inside), so no warp diverges ahead of the barrier
 #pragma unroll 1
     for (int i0 = 0; i0 < L.obs_pairs; i0 += nthreads) {
         const int i = i0 + threadIdx.x;
         if (i < L.obs_pairs) sObs[i] = (i < p.n_obs) ? make_float2(p.obs[2 * i], p.obs[2 * i + 1]) : make_float2(0.f, 0.f);
+    }
+    if constexpr (KS) {
+        const unsigned bar = smem_u32(&tma_bar);
+        unsigned done = 0;
+        while (!done) {
+            asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.b32 %0, 1, 0, P1;\n\t}"
+                         : "=r"(done) : "r"(bar), "r"(0u) : "memory");
+        }
     }
     __syncthreads();
 }
@@ -185,8 +210,13 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
 #pragma unroll
     for (int b = 0; b < 3; ++b) { a[b] = bc2(0.0f); d[b] = bc2(0.0f); }
     bool boot = true;          // first trip: nothing to contract yet, just fill the slot through the common tail
+#ifdef FGD_PHASE_CLOCKS
+    long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pc_t = clock64();
+#endif
     for (;;) {
         f2 y1[3], y2[3];
+        const bool was_back = (kind == K_BACK);
+        (void)was_back;
         if (!boot) {
             if (kind == K_IDLE) break;
             G.sync();                                                                    // operands complete
@@ -194,6 +224,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
             else { load_nz<WPT>(G, nz); contract_back<WPT, KS>(ko, kd, T, XA, XB, nz, y1, y2); }   // backward: K G_q + dK (-G_v)
             G.sync();                                                                    // operands consumed
         }
+        PCLK(was_back ? 4 : 0);
         TRACE("lane %d trip boot=%d kind=%d\n", threadIdx.x, (int)boot, kind);
         bool want_cand = false;     // write the next candidate into XA
         bool want_head = false;     // go to the head of the inner loop
@@ -231,6 +262,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
             float loss_c, toc_c;
             int ful_c;
             cost_phase<WPT, STRICT>(p, sObs, G, y1, y2, st.start, st.goal, st.lam_sg, st.lam_jl, Rw, loss_c, toc_c, ful_c);
+            PCLK(1);
             bool accept = false;
             if (kind == K_EVAL0) {
                 st.loss = loss_c; st.toc = toc_c; st.ful = ful_c;
@@ -274,6 +306,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
             }
             if (accept) grad_phase<WPT>(p, G, Rw, st.start, st.goal, st.lam_sg, st.lam_jl, XA, XB, nz);
         }
+        PCLK(was_back ? 5 : 2);
         // ---- common tail: loop heads, retirement, refill -------------------------------------
         bool save_active = false;
         if (want_head) {                                         // optimizer_BLS.py:155-157
@@ -316,7 +349,15 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
             write_rows<WPT>(p, G, c, XA);
         }
         boot = false;
+        PCLK(was_back ? 6 : 3);
+#ifdef FGD_PHASE_CLOCKS
+        pc[7] += 1;
+#endif
     }
+#ifdef FGD_PHASE_CLOCKS
+    if (p.dbg && blockIdx.x == 0 && G.tl == 0 && pc[7] > 2)
+        for (int i = 0; i < 8; ++i) p.dbg[i] = (int)(pc[i] >> 4);      // units of 16 cycles
+#endif
 }
 
 // ---------------------------------------------------------------------------

@@ -113,6 +113,10 @@ def test_eval_lambda_max_override(cuda_ready):
     ("bls", 1, 33, 11, 24, {}),
     ("bls", 2, 100, 40, 48, {"max_inner_iteration": 40, "max_outer_iteration": 3}),
     ("bls", 4, 256, 200, 16, {"max_inner_iteration": 12, "max_outer_iteration": 2}),
+    ("bls", 2, 65, 11, 40, {"max_inner_iteration": 30, "max_outer_iteration": 2}),
+    ("gd", 2, 128, 25, 32, {"max_inner_iteration": 25, "max_outer_iteration": 2}),
+    ("bls", 4, 129, 17, 24, {"max_inner_iteration": 20, "max_outer_iteration": 2}),
+    ("gd", 4, 200, 64, 20, {"max_inner_iteration": 15, "max_outer_iteration": 1}),
     ("bls", 1, 50, 11, 64, {"constraint_violating_dependant_loss": False, "lambda_max_cost": 0.25}),
 ])
 def test_optimize_bit_exact_strict(cuda_ready, mode, wpt, T, n_obs, B, over):

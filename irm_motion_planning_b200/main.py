@@ -68,6 +68,8 @@ def build_parser() -> argparse.ArgumentParser:
     ap.add_argument("--n-obstacles", type=int, default=0, help="0: the reference scene; N>0: N random obstacles")
     ap.add_argument("--obstacle-capacity", type=int, default=1024, help="size of the device obstacle buffer")
     ap.add_argument("--strict-math", type=_flag, default=False, help="IEEE reciprocal instead of rcp.approx")
+    ap.add_argument("--replan", type=int, default=0,
+                    help="after the timed runs: N warm-started re-plans on a drifting obstacle set (blog: 50 Hz re-planning)")
     return ap
 
 
@@ -150,11 +152,46 @@ def main(argv=None):
     print("result cost: ( avg", avg_result_cost, ", max", max_result_cost, "). constraint fulfiled",
           tr.constraintsFulfilledVerbose(result_alpha, start_c, goal_c, verbose=True))
 
+    if args.replan > 0:
+        _replan_demo(args, optimizer, batch_inputs)
+
     np.savetxt("trajectory_result.txt", np.array(tr.evaluate(result_alpha, tr.km, tr.jac)))
     if args.extended_vis and p is not None:
         p_np = np.array(p)
         print(p_np.shape)
         np.savetxt("trajectory_series.txt", p_np.reshape((-1, args.n_joints * int(args.n_timesteps))))
+
+
+def _replan_demo(args, optimizer, batch_inputs):
+    """--replan N: the obstacles drift a little every step; each step re-optimises from the previous
+    solution (WarmStartPlanner) and, for comparison, from the reference's cold start."""
+    import torch
+
+    from .replan import WarmStartPlanner
+    rng = np.random.default_rng(args.seed + 7)
+    env = optimizer.env
+    if batch_inputs is None:
+        start, goal, alpha0 = env.start_config[None], env.goal_config[None], None
+    else:
+        alpha0, start, goal = batch_inputs
+    obstacles = np.asarray(env.obstacles, np.float32).copy()
+    planner = WarmStartPlanner(optimizer, start, goal, alpha0)
+    planner.update(obstacles)                                  # first plan = the cold start
+    torch.cuda.synchronize()
+    warm_ms, warm_it, cold_it, ok = [], [], [], []
+    for _ in range(args.replan):
+        obstacles = (obstacles + rng.normal(0.0, 0.03, obstacles.shape)).astype(np.float32)
+        t0 = time.time()
+        res = planner.update(obstacles)
+        torch.cuda.synchronize()
+        warm_ms.append(1000 * (time.time() - t0))
+        warm_it.append(float(res.inner_iterations.mean())); ok.append(float(res.fulfilled.mean()))
+        cold = optimizer.optimize_batch(planner.trajectory.initTrajectory(start, goal).reshape(-1, planner.trajectory.N_timesteps, 3),
+                                        start, goal, obstacles)
+        cold_it.append(float(cold.inner_iterations.mean()))
+    print(f"re-planning x{args.replan} ({planner.B} trajectories): {np.mean(warm_ms):.3f} ms per plan "
+          f"({1000 / np.mean(warm_ms):.0f} Hz), inner iterations warm {np.mean(warm_it):.1f} vs cold {np.mean(cold_it):.1f}, "
+          f"constraints fulfilled {100 * np.mean(ok):.0f} %")
 
 
 if __name__ == "__main__":

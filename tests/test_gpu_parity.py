@@ -259,6 +259,28 @@ def test_device_init_trajectory_bit_exact_and_optimisable(cuda_ready, T, B):
         assert np.array_equal(is_.cpu().numpy(), cis) and np.array_equal(a.cpu().numpy(), ca)
 
 
+def test_warm_start_replanning_bit_exact(cuda_ready):
+    """a stream of scene updates, every plan warm-started from the previous solution through
+    the persistent handle (async obstacle upload, no re-creation); the oracle applies the same schedule."""
+    from irm_motion_planning_b200.batch import BatchedFGD
+    from irm_motion_planning_b200.replan import WarmStartPlanner
+    args, tr, obs, start, goal, alpha0 = _setup(B=12, seed=21)
+    opt = type("Opt", (), {"trajectory": tr, "engine": BatchedFGD(tr, "bls")})()
+    planner = WarmStartPlanner(opt, start, goal, alpha0)
+    rng = np.random.default_rng(3)
+    h0 = tr.handle
+    ca = alpha0
+    for step in range(4):
+        obs = (np.asarray(obs, np.float32) + rng.normal(0, 0.05, np.shape(obs))).astype(np.float32)
+        res = planner.update(obs)
+        ca, cfs, cis = _mirror(args, tr, obs, "bls").optimize(ca, start, goal)
+        assert np.array_equal(res.istate.cpu().numpy(), cis), step
+        assert np.array_equal(res.alpha.cpu().numpy(), ca), step
+        assert np.array_equal(res.fstate.cpu().numpy()[:, :6], cfs[:, :6]), step
+    assert tr.handle is h0 and planner.plans == 4
+    assert planner.trajectory_points(0).shape == (50, 3)
+
+
 def test_argmin_per_problem(cuda_ready):
     import torch
     from irm_motion_planning_b200.batch import BatchedFGD, BatchResult

@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--strict-math", action="store_true")
+    ap.add_argument("--whole-arm", action="store_true", help="obstacle cost over all joint positions (SURVEY 8f-3) instead of the end effector")
     ap.add_argument("--no-saturated", action="store_true", help="skip the secondary large-batch measurement of the default run")
     ap.add_argument("--saturated-batch", type=int, default=65536)
     return ap.parse_args()
@@ -138,6 +139,7 @@ def run_reference(a, rank, world):
     from irm_motion_planning_b200.trajectory import Trajectory
     from irm_motion_planning_b200.workloads import initial_alpha, make_workload
     wl = make_workload(a.workload, B=a.batch or None, seed=a.seed)
+    wl.args.whole_arm_cost = bool(a.whole_arm)
     traj = Trajectory(wl.args, create_handle=False)
     alpha0, start, goal = initial_alpha(wl, traj, a.seed)
     # each step: a bounded sample, sized so the whole run stays within a few minutes
@@ -160,7 +162,8 @@ def run_reference(a, rank, world):
 
 def config_dict(wl, traj, B, **extra):
     d = {"workload": f"{wl.name}: {wl.description}", "optimizer": wl.mode, "trajectories_per_gpu": int(B),
-         "n_timesteps": traj.N_timesteps, "n_obstacles": int(len(wl.obstacles)), "l2_flush_between_steps": True}
+         "n_timesteps": traj.N_timesteps, "n_obstacles": int(len(wl.obstacles)), "l2_flush_between_steps": True,
+         "obstacle_cost": "whole arm (3 joint positions)" if getattr(wl.args, "whole_arm_cost", False) else "end effector"}
     d.update(extra)
     return d
 
@@ -195,6 +198,8 @@ def main():
 
     strong = a.workload == "c5"
     wl = make_workload(a.workload, B=a.batch or None, seed=a.seed + (0 if strong else rank))
+    wl.args.whole_arm_cost = bool(a.whole_arm)
+    joints = 3 if a.whole_arm else 1
     traj = Trajectory(wl.args, strict_math=a.strict_math)
     traj.set_obstacles(wl.obstacles)
     alpha0, start, goal = initial_alpha(wl, traj, a.seed + (0 if strong else rank))
@@ -280,7 +285,7 @@ def main():
     outer = np.maximum(1, is_[:, backend.I_OUTER] + is_[:, backend.I_FULFILLED])
     assert (is_[:, backend.I_STATUS] == backend.ST_DONE).all(), "a timed step left unfinished trajectories"
     O_eff = len(wl.obstacles)
-    flops_step = flops_total(wl.mode, T, O_eff, inner, cand, outer)
+    flops_step = flops_total(wl.mode, T, O_eff, inner, cand, outer, joints)
     counts = torch.tensor([float(B), float(inner.sum()), flops_step], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(counts, op=dist.ReduceOp.SUM)
@@ -351,6 +356,7 @@ def main():
     saturated = None
     if world == 1 and not a.no_saturated and not a.batch and a.workload == "c2":
         wl2 = make_workload(a.workload, B=a.saturated_batch, seed=a.seed)
+        wl2.args.whole_arm_cost = bool(a.whole_arm)
         al2, st2, go2 = initial_alpha(wl2, traj, a.seed)
         B2 = len(al2)
         a2 = torch.as_tensor(al2, device=dev); s2 = torch.as_tensor(st2, device=dev).contiguous(); g2 = torch.as_tensor(go2, device=dev).contiguous()
@@ -365,7 +371,7 @@ def main():
                 ms2.append(e0.elapsed_time(e1)); st_last = is2.cpu().numpy()
         t2 = sum(ms2) / len(ms2) * 1e-3
         fl2 = flops_total(wl2.mode, T, len(wl2.obstacles), st_last[:, backend.I_INNER_TOTAL], st_last[:, backend.I_CAND_EVALS],
-                          np.maximum(1, st_last[:, backend.I_OUTER] + st_last[:, backend.I_FULFILLED]))
+                          np.maximum(1, st_last[:, backend.I_OUTER] + st_last[:, backend.I_FULFILLED]), joints)
         saturated = {"trajectories_per_gpu": int(B2), "steps": len(ms2), "ms_per_step": 1e3 * t2, "value": B2 / t2, "unit": UNIT,
                      "fgd_iters_per_s": float(st_last[:, backend.I_INNER_TOTAL].sum()) / t2,
                      "roofline_frac": fl2 / t2 * 1e-12 / peak if peak else None,

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define FGD_ABI_VERSION 1
+#define FGD_ABI_VERSION 2
 #define FGD_MAX_T 256            /* time samples / RKHS support points            */
 #define FGD_MAX_OUTER 16         /* length of the gd_lr table                     */
 #define FGD_FSTATE 8             /* floats of resumable state per trajectory      */
@@ -71,6 +71,9 @@ typedef struct FgdConfig {
     int32_t max_bls_iteration;           /* optimizer_BLS.py:39                              */
     int32_t constraint_violating_dependant_loss; /* trajectory.py:28                         */
     int32_t n_gd_lr;                     /* valid entries of gd_lr   optimizer_GD.py:34-38   */
+    int32_t whole_arm_cost;              /* 0: the reference's end-effector obstacle cost (trajectory.py:113-126);
+                                            1: summed over all joint positions fk_1..fk_3 (robot.py:39-72), the
+                                            extension named in DevBlog-Theme/blog-post.html:505-513              */
     float lambda_sg_constraint, lambda_jl_constraint, lambda_constraint_increase;   /* optimizer_BLS.py:32-34 */
     float lambda_max_cost, lambda_reg;                                              /* optimizer_BLS.py:36-37 */
     float loop_loss_reduction;                                                      /* optimizer_BLS.py:30    */

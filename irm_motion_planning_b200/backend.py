@@ -15,7 +15,7 @@ import numpy as np
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FGD_LIBRARY", os.path.join(_PKG, "libfgd_b200.so"))   # override: debugging builds only
 
-FGD_ABI_VERSION = 1
+FGD_ABI_VERSION = 2
 FGD_MAX_T = 256
 FGD_MAX_OUTER = 16
 FSTATE, ISTATE = 8, 8
@@ -34,7 +34,7 @@ class FgdConfig(C.Structure):
     _fields_ = (
         [(n, C.c_int32) for n in ("abi_version", "n_timesteps", "n_joints", "obstacle_capacity", "strict_math",
                                   "max_inner_iteration", "max_outer_iteration", "max_bls_iteration",
-                                  "constraint_violating_dependant_loss", "n_gd_lr")]
+                                  "constraint_violating_dependant_loss", "n_gd_lr", "whole_arm_cost")]
         + [(n, C.c_float) for n in ("lambda_sg_constraint", "lambda_jl_constraint", "lambda_constraint_increase",
                                     "lambda_max_cost", "lambda_reg", "loop_loss_reduction", "eps_position",
                                     "eps_velocity", "bls_lr_start", "bls_alpha", "bls_beta_plus", "bls_beta_minus",
@@ -115,6 +115,7 @@ def make_config(hp, km: np.ndarray, dkm: np.ndarray, jac: np.ndarray, obstacle_c
     c.constraint_violating_dependant_loss = int(bool(hp.constraint_violating_dependant_loss))
     lrs = [float(x) for x in hp.gd_lr][:FGD_MAX_OUTER]
     c.n_gd_lr = len(lrs)
+    c.whole_arm_cost = int(bool(getattr(hp, "whole_arm_cost", False)))
     for i, x in enumerate(lrs):
         c.gd_lr[i] = x
     c.lambda_sg_constraint = hp.lambda_sg_constraint

@@ -53,30 +53,30 @@ inline int warps_per_trajectory(int T) { return T <= 64 ? 1 : (T <= 128 ? 2 : 4)
     X(0, 1, true, 8, 2) X(0, 2, false, 2, 8) X(0, 4, false, 4, 4) \
     X(1, 1, true, 4, 4) X(1, 2, false, 2, 6) X(1, 4, false, 4, 3)
 
-template <int WPT, bool STRICT, bool KS, int NW, int MINB>
+template <int WPT, bool STRICT, bool KS, int NW, int MINB, bool ARM>
 cudaError_t launch_opt(const DevParams &p, int grid, size_t smem, cudaStream_t st)
 {
-    auto kern = fgd_optimize_kernel<WPT, STRICT, KS, NW, MINB>;
+    auto kern = fgd_optimize_kernel<WPT, STRICT, KS, NW, MINB, ARM>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, NW * 32, smem, st>>>(p);
     return cudaGetLastError();
 }
 
-template <int WPT, bool STRICT, bool KS, int NW, int MINB>
+template <int WPT, bool STRICT, bool KS, int NW, int MINB, bool ARM>
 int occupancy_opt(size_t smem)
 {
-    auto kern = fgd_optimize_kernel<WPT, STRICT, KS, NW, MINB>;
+    auto kern = fgd_optimize_kernel<WPT, STRICT, KS, NW, MINB, ARM>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int nb = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, NW * 32, smem) != cudaSuccess) nb = 1;
     return nb < 1 ? 1 : nb;
 }
 
-template <int WPT, bool STRICT, bool KS, int NW>
+template <int WPT, bool STRICT, bool KS, int NW, bool ARM>
 cudaError_t launch_eval(const DevParams &p, const EvalPtrs &e, int grid, size_t smem, cudaStream_t st)
 {
-    auto kern = fgd_eval_kernel<WPT, STRICT, KS, NW>;
+    auto kern = fgd_eval_kernel<WPT, STRICT, KS, NW, ARM>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     kern<<<grid, NW * 32, smem, st>>>(p, e);
@@ -99,33 +99,38 @@ int warps_per_cta(int v, int WPT)
     return WPT;
 }
 
-cudaError_t dispatch_opt(int v, int WPT, bool strict, const DevParams &p, int grid, size_t smem, cudaStream_t st)
+cudaError_t dispatch_opt(int v, int WPT, bool strict, bool arm, const DevParams &p, int grid, size_t smem, cudaStream_t st)
 {
 #define X(V_, W_, KS_, NW_, MB_)                                                        \
     if (v == V_ && WPT == W_)                                                            \
-        return strict ? launch_opt<W_, true, KS_, NW_, MB_>(p, grid, smem, st)           \
-                      : launch_opt<W_, false, KS_, NW_, MB_>(p, grid, smem, st);
+        return arm ? (strict ? launch_opt<W_, true, KS_, NW_, MB_, true>(p, grid, smem, st)      \
+                             : launch_opt<W_, false, KS_, NW_, MB_, true>(p, grid, smem, st))    \
+                   : (strict ? launch_opt<W_, true, KS_, NW_, MB_, false>(p, grid, smem, st)     \
+                             : launch_opt<W_, false, KS_, NW_, MB_, false>(p, grid, smem, st));
     FGD_FOR_CONFIGS(X)
 #undef X
     return cudaErrorInvalidValue;
 }
 
-int dispatch_occ(int v, int WPT, bool strict, size_t smem)
+int dispatch_occ(int v, int WPT, bool strict, bool arm, size_t smem)
 {
 #define X(V_, W_, KS_, NW_, MB_)                                                        \
     if (v == V_ && WPT == W_)                                                            \
-        return strict ? occupancy_opt<W_, true, KS_, NW_, MB_>(smem) : occupancy_opt<W_, false, KS_, NW_, MB_>(smem);
+        return arm ? (strict ? occupancy_opt<W_, true, KS_, NW_, MB_, true>(smem) : occupancy_opt<W_, false, KS_, NW_, MB_, true>(smem))   \
+                   : (strict ? occupancy_opt<W_, true, KS_, NW_, MB_, false>(smem) : occupancy_opt<W_, false, KS_, NW_, MB_, false>(smem));
     FGD_FOR_CONFIGS(X)
 #undef X
     return 1;
 }
 
-cudaError_t dispatch_eval(int WPT, bool strict, const DevParams &p, const EvalPtrs &e, int grid, size_t smem, cudaStream_t st)
+cudaError_t dispatch_eval(int WPT, bool strict, bool arm, const DevParams &p, const EvalPtrs &e, int grid, size_t smem, cudaStream_t st)
 {
 #define X(V_, W_, KS_, NW_, MB_)                                                        \
     if (V_ == 0 && WPT == W_)                                                            \
-        return strict ? launch_eval<W_, true, KS_, NW_>(p, e, grid, smem, st)            \
-                      : launch_eval<W_, false, KS_, NW_>(p, e, grid, smem, st);
+        return arm ? (strict ? launch_eval<W_, true, KS_, NW_, true>(p, e, grid, smem, st)       \
+                             : launch_eval<W_, false, KS_, NW_, true>(p, e, grid, smem, st))     \
+                   : (strict ? launch_eval<W_, true, KS_, NW_, false>(p, e, grid, smem, st)      \
+                             : launch_eval<W_, false, KS_, NW_, false>(p, e, grid, smem, st));
     FGD_FOR_CONFIGS(X)
 #undef X
     return cudaErrorInvalidValue;
@@ -138,7 +143,7 @@ Geometry geometry(const FgdHandle *h, int B, int n_obs)
     const int teams = nw / h->WPT;
     g.block = nw * 32;
     g.smem = (int)make_layout(h->T, h->TP, n_obs, h->k_in_smem, teams, h->WPT).bytes();
-    const int occ = dispatch_occ(h->variant, h->WPT, h->cfg.strict_math != 0, (size_t)g.smem);
+    const int occ = dispatch_occ(h->variant, h->WPT, h->cfg.strict_math != 0, h->cfg.whole_arm_cost != 0, (size_t)g.smem);
     const long long need = ((long long)B + teams - 1) / teams;
     const long long cap = (long long)occ * h->num_sms;
     g.grid = (int)(need < cap ? need : cap);
@@ -178,7 +183,7 @@ int run_optimize(FgdHandle *h, int mode, int B, float *d_alpha, const float *d_s
     fill_params(h, p, mode, B, d_alpha, d_start, d_goal, d_fstate, d_istate, budget);
     const Geometry g = geometry(h, B, p.n_obs);
     CK(cudaMemsetAsync(h->d_queue, 0, sizeof(unsigned), st));
-    CK(dispatch_opt(h->variant, h->WPT, h->cfg.strict_math != 0, p, g.grid, (size_t)g.smem, st));
+    CK(dispatch_opt(h->variant, h->WPT, h->cfg.strict_math != 0, h->cfg.whole_arm_cost != 0, p, g.grid, (size_t)g.smem, st));
     h->launches += 1;
     CK(cudaEventRecord(h->launch_event, st));
     h->launch_event_pending = true;
@@ -356,7 +361,7 @@ int fgd_eval_cost_grad(FgdHandle *h, int32_t B, const float *d_alpha, const floa
     const size_t smem = make_layout(h->T, h->TP, p.n_obs, h->k_in_smem, per_cta, h->WPT).bytes();
     long long need = ((long long)B + per_cta - 1) / per_cta, cap = (long long)h->num_sms * 4;
     const int grid = (int)(need < cap ? need : cap);
-    CK(dispatch_eval(h->WPT, h->cfg.strict_math != 0, p, e, grid, smem, st));
+    CK(dispatch_eval(h->WPT, h->cfg.strict_math != 0, h->cfg.whole_arm_cost != 0, p, e, grid, smem, st));
     h->launches += 1;
     return FGD_OK;
 }

@@ -150,7 +150,10 @@ __device__ __forceinline__ float ss3(float a, float b, float c) { return fmaf(c,
 // are handled as R/2 row pairs: .x = row 2p, .y = row 2p+1.  Every packed
 // instruction is two independent IEEE-754 round-to-nearest operations, so the
 // results are bit-identical to the scalar sequence of the mirror oracle while
-// the instruction count per row halves.  Scalars (constants, obstacle
+// the instruction count per row halves.  Caveat (seen in SASS): ptxas contracts an
+// __fmul2_rn feeding an __fadd2_rn into one FFMA2 even under -fmad=false, so a
+// product that is added to something is always written as an explicit fma2() here
+// and as fmaf() in the oracle; mul2 results only feed multiplies, selects or stores.  Scalars (constants, obstacle
 // coordinates, operand rows) enter through the .F32 broadcast operand form.
 // ---------------------------------------------------------------------------
 typedef float2 f2;
@@ -296,10 +299,13 @@ __device__ __forceinline__ void contract_back(const float *__restrict__ ko, cons
     }
 }
 
-// Per-thread row pair kept between the cost phase and the gradient phase.
+// Per-thread row pair kept between the cost phase and the gradient phase.  ARM (whole-arm obstacle cost,
+// DevBlog-Theme/blog-post.html:505-513): the potential's gradient at the three joint positions fk_1, fk_2,
+// fk_3 (robot.py:39-72); otherwise only at the end effector fk_3 = fk (index 0).
+template <bool ARM>
 struct Rows {
     f2 q[3], v[3], sn[3], cs[3];
-    f2 gx, gy;
+    f2 gx[ARM ? 3 : 1], gy[ARM ? 3 : 1];
     int amax;
 };
 
@@ -364,20 +370,22 @@ __device__ __forceinline__ void obstacle_block(const float2 *__restrict__ obs, c
 // The obstacle loop accumulates sum 1/(2 den) and sum d/(2 den)^2; the constant factors
 // 0.8 and -0.8 of environment.py:43,57 (times 2 and 4) are applied once per sample.
 // ---------------------------------------------------------------------------
-template <int WPT, bool STRICT>
+template <int WPT, bool STRICT, bool ARM>
 __device__ __forceinline__ void cost_phase(const DevParams &p, const float2 *__restrict__ sObs, const Team<WPT> &G,
                                            const f2 (&yq)[3], const f2 (&yv)[3],
                                            const float *start, const float *goal, float lam_sg, float lam_jl,
-                                           Rows &Rw, float &loss, float &toc, int &ful)
+                                           Rows<ARM> &Rw, float &loss, float &toc, int &ful)
 {
+    constexpr int NJ = ARM ? 3 : 1;                        // joint positions charged with the obstacle potential
     const int T = p.T;
     const int t0 = G.tl * R;
     const int lT = (T - 1) / R, rT = (T - 1) % R;          // team thread / row slot owning sample T-1
     const bool valid0 = t0 < T, valid1 = (t0 + 1) < T;
     float part_p = 0.0f, part_v = 0.0f;
     row_kinematics(p, yq, yv, Rw.q, Rw.v, Rw.sn, Rw.cs);
-    const f2 x = fma2(bc2(p.link[2]), Rw.cs[2], fma2(bc2(p.link[1]), Rw.cs[1], mul2(bc2(p.link[0]), Rw.cs[0])));     // robot.py:33
-    const f2 y = fma2(bc2(p.link[2]), Rw.sn[2], fma2(bc2(p.link[1]), Rw.sn[1], mul2(bc2(p.link[0]), Rw.sn[0])));     // robot.py:34
+    f2 px[3], py[3];                                       // fk_1, fk_2, fk_3 = fk      robot.py:33-34, 39-72
+    px[0] = mul2(bc2(p.link[0]), Rw.cs[0]); px[1] = fma2(bc2(p.link[1]), Rw.cs[1], px[0]); px[2] = fma2(bc2(p.link[2]), Rw.cs[2], px[1]);
+    py[0] = mul2(bc2(p.link[0]), Rw.sn[0]); py[1] = fma2(bc2(p.link[1]), Rw.sn[1], py[0]); py[2] = fma2(bc2(p.link[2]), Rw.sn[2], py[1]);
     // joint-limit penalties and limit predicates of these rows   trajectory.py:215-255, robot.py:104-113
     f2 e3[3], f3[3];
     bool ok0 = true, ok1 = true;
@@ -412,16 +420,30 @@ __device__ __forceinline__ void cost_phase(const DevParams &p, const float2 *__r
         sspT = ss3(Rw.q[0].y - goal[0], Rw.q[1].y - goal[1], Rw.q[2].y - goal[2]);
         ssvT = ss3(Rw.v[0].y, Rw.v[1].y, Rw.v[2].y);
     }
-    // obstacle potential: both samples of this thread against every obstacle, in blocks of 4
-    f2 sr = bc2(0.0f), sx = bc2(0.0f), sy = bc2(0.0f);
+    // obstacle potential: both samples of this thread (at NJ joint positions) against every obstacle, in blocks of 4
+    f2 sr[NJ], sx[NJ], sy[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) { sr[j] = bc2(0.0f); sx[j] = bc2(0.0f); sy[j] = bc2(0.0f); }
     const int n_obs = p.n_obs;
     int o = 0;
 #pragma unroll 1
-    for (; o + 4 <= n_obs; o += 4) obstacle_block<4, STRICT>(sObs + o, x, y, sr, sx, sy);
-    if (o + 2 <= n_obs) { obstacle_block<2, STRICT>(sObs + o, x, y, sr, sx, sy); o += 2; }
-    if (o < n_obs) obstacle_block<1, STRICT>(sObs + o, x, y, sr, sx, sy);
-    const f2 cost = mul2(bc2(1.6f), sr);
-    Rw.gx = mul2(bc2(-3.2f), sx); Rw.gy = mul2(bc2(-3.2f), sy);
+    for (; o + 4 <= n_obs; o += 4) {
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) obstacle_block<4, STRICT>(sObs + o, px[3 - NJ + j], py[3 - NJ + j], sr[j], sx[j], sy[j]);
+    }
+    if (o + 2 <= n_obs) {
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) obstacle_block<2, STRICT>(sObs + o, px[3 - NJ + j], py[3 - NJ + j], sr[j], sx[j], sy[j]);
+        o += 2;
+    }
+    if (o < n_obs) {
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) obstacle_block<1, STRICT>(sObs + o, px[3 - NJ + j], py[3 - NJ + j], sr[j], sx[j], sy[j]);
+    }
+    f2 cost = mul2(bc2(1.6f), sr[0]);
+    if constexpr (ARM) cost = fma2(bc2(1.6f), sr[2], fma2(bc2(1.6f), sr[1], cost));      // c_1 + c_2 + c_3, explicit fmas as in the oracle
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) { Rw.gx[j] = mul2(bc2(-3.2f), sx[j]); Rw.gy[j] = mul2(bc2(-3.2f), sy[j]); }
     float part_c = 0.0f, lmax = 0.0f;                 // cost >= 0
     if (valid0) { part_c = part_c + cost.x; lmax = fmaxf(lmax, cost.x); }
     if (valid1) { part_c = part_c + cost.y; lmax = fmaxf(lmax, cost.y); }
@@ -484,15 +506,16 @@ __device__ __forceinline__ void cost_phase(const DevParams &p, const float2 *__r
 // the warp masks go through the team scratch and are read back after the team
 // barrier that precedes the backward contraction (load_nz).
 // ---------------------------------------------------------------------------
-template <int WPT>
-__device__ __forceinline__ void grad_phase(const DevParams &p, const Team<WPT> &G, const Rows &Rw, const float *start, const float *goal,
+template <int WPT, bool ARM>
+__device__ __forceinline__ void grad_phase(const DevParams &p, const Team<WPT> &G, const Rows<ARM> &Rw, const float *start, const float *goal,
                                            float lam_sg, float lam_jl, float4 *XA, float4 *XB, unsigned (&nz)[WPT][R])
 {
+    constexpr int NJ = ARM ? 3 : 1;
     const int T = p.T;
     const int ta = G.tl * R, tb = ta + 1;
     const float w_hi = p.lam_max + p.w_avg;
     const f2 wt = mk2((ta == Rw.amax) ? w_hi : p.w_avg, (tb == Rw.amax) ? w_hi : p.w_avg);
-    const f2 cgx = mul2(wt, Rw.gx), cgy = mul2(wt, Rw.gy);
+    const f2 cgx = mul2(wt, Rw.gx[NJ - 1]), cgy = mul2(wt, Rw.gy[NJ - 1]);
     f2 xs[3], ys[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) { xs[k] = neg2(mul2(bc2(p.link[k]), Rw.sn[k])); ys[k] = mul2(bc2(p.link[k]), Rw.cs[k]); }
@@ -505,7 +528,14 @@ __device__ __forceinline__ void grad_phase(const DevParams &p, const Team<WPT> &
     for (int k = 0; k < 3; ++k) {
         const f2 Jx = sub2(add2(xs[k], Sx), Cx[k]);
         const f2 Jy = sub2(add2(ys[k], Sy), Cy[k]);
-        const f2 tg = fma2(cgy, Jy, mul2(cgx, Jx));
+        f2 tg = fma2(cgy, Jy, mul2(cgx, Jx));
+        if constexpr (ARM) {                                   // + joints 2 and 1: J_j[k] = sum_{m = k..j}
+            if (k <= 1) {
+                const f2 J2x = (k == 0) ? add2(xs[0], xs[1]) : xs[1], J2y = (k == 0) ? add2(ys[0], ys[1]) : ys[1];
+                tg = fma2(mul2(wt, Rw.gy[1]), J2y, fma2(mul2(wt, Rw.gx[1]), J2x, tg));
+            }
+            if (k == 0) tg = fma2(mul2(wt, Rw.gy[0]), ys[0], fma2(mul2(wt, Rw.gx[0]), xs[0], tg));
+        }
         const f2 qk = Rw.q[k], vk = Rw.v[k];
         f2 sgp, sgv;
         sgp.x = a0 ? (qk.x - start[k]) : (aT ? (qk.x - goal[k]) : 0.0f);

@@ -180,7 +180,7 @@ __device__ __forceinline__ void stage_constants(const DevParams &p, const SmemLa
 // (candidate evaluation or gradient).  NW warps per CTA; WPT > 1 requires
 // NW == WPT (the CTA barrier is the team barrier).
 // ---------------------------------------------------------------------------
-template <int WPT, bool STRICT, bool KS, int NW, int MINB>
+template <int WPT, bool STRICT, bool KS, int NW, int MINB, bool ARM>
 __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __grid_constant__ DevParams p)
 {
     static_assert(WPT == 1 || NW == WPT, "multi-warp teams own their CTA");
@@ -258,10 +258,10 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
             kind = K_CAND;
         } else if (!boot) {
             // ---- loss (and, if accepted, gradient operands) at alpha or at a candidate -------
-            Rows Rw;
+            Rows<ARM> Rw;
             float loss_c, toc_c;
             int ful_c;
-            cost_phase<WPT, STRICT>(p, sObs, G, y1, y2, st.start, st.goal, st.lam_sg, st.lam_jl, Rw, loss_c, toc_c, ful_c);
+            cost_phase<WPT, STRICT, ARM>(p, sObs, G, y1, y2, st.start, st.goal, st.lam_sg, st.lam_jl, Rw, loss_c, toc_c, ful_c);
             PCLK(1);
             bool accept = false;
             if (kind == K_EVAL0) {
@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
                     else { st.inner += 1; want_head = true; }
                 }
             }
-            if (accept) grad_phase<WPT>(p, G, Rw, st.start, st.goal, st.lam_sg, st.lam_jl, XA, XB, nz);
+            if (accept) grad_phase<WPT, ARM>(p, G, Rw, st.start, st.goal, st.lam_sg, st.lam_jl, XA, XB, nz);
         }
         PCLK(was_back ? 5 : 2);
         // ---- common tail: loop heads, retirement, refill -------------------------------------
@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
 // Evaluation only (unit-parity hook and the host's compute_trajectory_cost*):
 // one team per trajectory, grid-stride.
 // ---------------------------------------------------------------------------
-template <int WPT, bool STRICT, bool KS, int NW>
+template <int WPT, bool STRICT, bool KS, int NW, bool ARM>
 __global__ void __launch_bounds__(NW * 32) fgd_eval_kernel(const __grid_constant__ DevParams p, const EvalPtrs e)
 {
     static_assert(WPT == 1 || NW == WPT, "multi-warp teams own their CTA");
@@ -397,10 +397,10 @@ __global__ void __launch_bounds__(NW * 32) fgd_eval_kernel(const __grid_constant
         G.sync();
         contract<WPT, KS, true>(kd, T, XA, XA, y1, y2);
         G.sync();
-        Rows Rw;
+        Rows<ARM> Rw;
         float loss, toc;
         int ful;
-        cost_phase<WPT, STRICT>(p, sObs, G, y1, y2, start, goal, e.lam_sg, e.lam_jl, Rw, loss, toc, ful);
+        cost_phase<WPT, STRICT, ARM>(p, sObs, G, y1, y2, start, goal, e.lam_sg, e.lam_jl, Rw, loss, toc, ful);
         if (G.tl == 0) {
             if (e.loss) e.loss[b] = loss;
             if (e.toc) e.toc[b] = toc;
@@ -419,7 +419,7 @@ __global__ void __launch_bounds__(NW * 32) fgd_eval_kernel(const __grid_constant
         }
         if (e.grad) {
             unsigned nz_unused[WPT][R];
-            grad_phase<WPT>(p, G, Rw, start, goal, e.lam_sg, e.lam_jl, XA, XB, nz_unused);
+            grad_phase<WPT, ARM>(p, G, Rw, start, goal, e.lam_sg, e.lam_jl, XA, XB, nz_unused);
             G.sync();
             contract<WPT, KS, false>(kd, T, XA, XB, y1, y2);      // dense reference form of the backward contraction
             f2 g[3];

@@ -68,6 +68,8 @@ def build_parser() -> argparse.ArgumentParser:
     ap.add_argument("--n-obstacles", type=int, default=0, help="0: the reference scene; N>0: N random obstacles")
     ap.add_argument("--obstacle-capacity", type=int, default=1024, help="size of the device obstacle buffer")
     ap.add_argument("--strict-math", type=_flag, default=False, help="IEEE reciprocal instead of rcp.approx")
+    ap.add_argument("--whole-arm-cost", type=_flag, default=False,
+                    help="obstacle cost summed over all joint positions instead of the end effector only (the reference blog's extension)")
     ap.add_argument("--replan", type=int, default=0,
                     help="after the timed runs: N warm-started re-plans on a drifting obstacle set (blog: 50 Hz re-planning)")
     return ap

@@ -110,22 +110,23 @@ def obstacle_swap(k: int, seed: int = 0, lo: int = 192, hi: int = 320) -> np.nda
 
 
 # algorithmic FLOPs: FMA = 2, divide = 1, sin/cos = 1 each, D = 3
-def flops_cost(T, O):
-    return 12 * T * T + 9 * T * O + 156 * T
+def flops_cost(T, O, joints=1):
+    return 12 * T * T + 9 * T * O * joints + 156 * T
 
 
-def flops_grad(T, O):
-    return 24 * T * T + 15 * T * O + 272 * T
+def flops_grad(T, O, joints=1):
+    return 24 * T * T + 15 * T * O * joints + 272 * T
 
 
-def flops_total(mode: str, T: int, O: int, inner_total, cand_evals, outer_bodies):
-    """Reference-algorithm FLOPs consumed by a batch (arrays of per-trajectory counters)."""
+def flops_total(mode: str, T: int, O: int, inner_total, cand_evals, outer_bodies, joints: int = 1):
+    """Reference-algorithm FLOPs consumed by a batch (arrays of per-trajectory counters).
+    joints = 3 for the whole-arm obstacle cost (three joint positions per sample)."""
     inner_total = np.asarray(inner_total, np.float64)
     cand = np.asarray(cand_evals, np.float64)
     outer = np.asarray(outer_bodies, np.float64)
     E = 6 * T * T + 18 * T
     if mode == "bls":
-        it = inner_total * (flops_grad(T, O) + 15 * T) + cand * flops_cost(T, O)
+        it = inner_total * (flops_grad(T, O, joints) + 15 * T) + cand * flops_cost(T, O, joints)
     else:
-        it = inner_total * (flops_grad(T, O) + 6 * T) + cand * flops_cost(T, O) + outer * flops_cost(T, O)
+        it = inner_total * (flops_grad(T, O, joints) + 6 * T) + cand * flops_cost(T, O, joints) + outer * flops_cost(T, O, joints)
     return float(np.sum(it + outer * (2 * E + 30 * T)))

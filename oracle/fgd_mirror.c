@@ -35,6 +35,11 @@
  *     to sum(g.T @ n)                              (optimizer_BLS.py:166)
  *   - sin/cos: Cody-Waite reduction + cephes minimax polynomials written out
  *     below (<= 2 ulp), instead of the platform libm.
+ *
+ * Extension (cfg.whole_arm, not in the reference's code; its blog, DevBlog-Theme/
+ * blog-post.html:505-513, names it): cost_v[t] = sum_j costmap(fk_j(q_t)) over the three
+ * joint positions (robot.py:39-72), summed with explicit fmas; gradient through the
+ * per-joint Jacobians.  Pinned by oracle/fgd_numpy.py (finite-difference checked in FP64).
  */
 #include <math.h>
 #include <stdint.h>
@@ -57,6 +62,7 @@ typedef struct {
     float link[3];
     float J[9];
     float gd_lr[16];
+    int whole_arm;      /* 1: obstacle cost summed over all joint positions fk_1..fk_3 (blog-post.html:505-513) */
 } MirrorCfg;
 
 /* state layout shared with the CUDA side (include/fgd_b200.h) */
@@ -175,7 +181,8 @@ static void evaluate_point(const MirrorCfg *c, const Derived *d, const float *K,
 {
     const int T = c->T;
     float qr[MAX_T * 3], vr[MAX_T * 3];
-    float costv[MAX_T], gx[MAX_T], gy[MAX_T], jp_row[MAX_T], jv_row[MAX_T];
+    float costv[MAX_T], gx[MAX_T][3], gy[MAX_T][3], jp_row[MAX_T], jv_row[MAX_T];
+    const int j_lo = c->whole_arm ? 0 : 2;                   /* joints whose position is charged */
     float sn[MAX_T][3], cs[MAX_T][3];
     contract(K, alpha, 1.0f, T, qr);                         /* trajectory.py:273 */
     contract(dK, alpha, 1.0f, T, vr);                        /* trajectory.py:274 */
@@ -191,19 +198,24 @@ static void evaluate_point(const MirrorCfg *c, const Derived *d, const float *K,
         mirror_sincos(c1, &sn[t][0], &cs[t][0]);
         mirror_sincos(c2, &sn[t][1], &cs[t][1]);
         mirror_sincos(c3, &sn[t][2], &cs[t][2]);
-        float x = fmaf(c->link[2], cs[t][2], fmaf(c->link[1], cs[t][1], c->link[0] * cs[t][0]));  /* robot.py:33 */
-        float y = fmaf(c->link[2], sn[t][2], fmaf(c->link[1], sn[t][1], c->link[0] * sn[t][0]));  /* robot.py:34 */
-        float sr = 0.0f, sx = 0.0f, sy = 0.0f;
-        for (int o = 0; o < c->n_obs; ++o) {                 /* environment.py:46-58 */
-            float dx = x - obs[2 * o], dy = y - obs[2 * o + 1];
-            float m = fmaf(dy, dy, fmaf(dx, dx, 1.0f));      /* 2 den = 1 + |f-o|^2  */
-            float r = 1.0f / m;
-            sr = sr + r;                                     /* sum 1/(2 den)        */
-            float r2 = r * r;
-            sx = fmaf(r2, dx, sx);                           /* sum d/(2 den)^2      */
-            sy = fmaf(r2, dy, sy);
+        float px[3], py[3], cj[3], srj[3];                           /* joint positions fk_1, fk_2, fk_3 = fk   robot.py:33-34, 39-72 */
+        px[0] = c->link[0] * cs[t][0]; px[1] = fmaf(c->link[1], cs[t][1], px[0]); px[2] = fmaf(c->link[2], cs[t][2], px[1]);
+        py[0] = c->link[0] * sn[t][0]; py[1] = fmaf(c->link[1], sn[t][1], py[0]); py[2] = fmaf(c->link[2], sn[t][2], py[1]);
+        for (int j = j_lo; j < 3; ++j) {
+            float sr = 0.0f, sx = 0.0f, sy = 0.0f;
+            for (int o = 0; o < c->n_obs; ++o) {             /* environment.py:46-58 */
+                float dx = px[j] - obs[2 * o], dy = py[j] - obs[2 * o + 1];
+                float m = fmaf(dy, dy, fmaf(dx, dx, 1.0f));  /* 2 den = 1 + |f-o|^2  */
+                float r = 1.0f / m;
+                sr = sr + r;                                 /* sum 1/(2 den)        */
+                float r2 = r * r;
+                sx = fmaf(r2, dx, sx);                       /* sum d/(2 den)^2      */
+                sy = fmaf(r2, dy, sy);
+            }
+            srj[j] = sr; cj[j] = 1.6f * sr; gx[t][j] = -3.2f * sx; gy[t][j] = -3.2f * sy;
         }
-        costv[t] = 1.6f * sr; gx[t] = -3.2f * sx; gy[t] = -3.2f * sy;
+        /* whole arm: c_1 + c_2 + c_3 as fma(1.6, s_3, fma(1.6, s_2, 1.6 * s_1)) */
+        costv[t] = c->whole_arm ? fmaf(1.6f, srj[2], fmaf(1.6f, srj[1], cj[0])) : cj[2];
         /* joint-limit penalties  trajectory.py:215-268 */
         float ep = 0.0f, ev = 0.0f;
         float e3[3], f3[3];
@@ -243,7 +255,7 @@ static void evaluate_point(const MirrorCfg *c, const Derived *d, const float *K,
     for (int t = 0; t < T; ++t) {
         const float *qt = q + t * 3, *vt = v + t * 3;
         float wt = (t == amax) ? (c->lam_max + d->w_avg) : d->w_avg;      /* trajectory.py:100-105 */
-        float cgx = wt * gx[t], cgy = wt * gy[t];
+        float cgx = wt * gx[t][2], cgy = wt * gy[t][2];
         float xs[3], ys[3];
         for (int k = 0; k < 3; ++k) { xs[k] = -(c->link[k] * sn[t][k]); ys[k] = c->link[k] * cs[t][k]; }   /* robot.py:80,83 */
         float Sx = (xs[0] + xs[1]) + xs[2], Sy = (ys[0] + ys[1]) + ys[2];
@@ -253,6 +265,13 @@ static void evaluate_point(const MirrorCfg *c, const Derived *d, const float *K,
             float Jx = (xs[k] + Sx) - Cx[k];                               /* robot.py:81 */
             float Jy = (ys[k] + Sy) - Cy[k];                               /* robot.py:84 */
             float tg = fmaf(cgy, Jy, cgx * Jx);                            /* trajectory.py:125 */
+            if (c->whole_arm) {                                            /* + joints 2 and 1: J_j[k] = sum_{m=k..j} */
+                if (k <= 1) {
+                    float J2x = (k == 0) ? xs[0] + xs[1] : xs[1], J2y = (k == 0) ? ys[0] + ys[1] : ys[1];
+                    tg = fmaf(wt * gy[t][1], J2y, fmaf(wt * gx[t][1], J2x, tg));
+                }
+                if (k == 0) tg = fmaf(wt * gy[t][0], ys[0], fmaf(wt * gx[t][0], xs[0], tg));
+            }
             float sgp = (t == 0) ? d0[k] : ((t == T - 1) ? dT[k] : 0.0f);
             float sgv = (t == 0 || t == T - 1) ? vt[k] : 0.0f;
             int m = c->cvdl ? (qt[k] > d->q_hi || qt[k] < d->q_lo) : 1;

@@ -73,6 +73,9 @@ class Hyper:
     max_joint_velocity: float = 7      # main.py:93
     max_joint_position: float = 2      # main.py:95
     min_joint_position: float = -1     # main.py:97
+    # extension named by the reference's blog (DevBlog-Theme/blog-post.html:505-513), not in its code:
+    # the obstacle cost of a sample is summed over ALL joint positions fk_j (robot.py:39-72)
+    whole_arm_cost: bool = False
 
 
 # --------------------------------------------------------------------------
@@ -197,6 +200,22 @@ class RobotModel:
         ry = y + np.sum(y, axis=1, dtype=self.dt)[:, None] - np.cumsum(y, axis=1, dtype=self.dt)
         return np.stack((rx, ry))
 
+    def fk_joint(self, q, j):                           # robot.py:39-72 (fk_joint_1/2/3), j = 1..3
+        c = np.cumsum(q.reshape(-1, 3)[:, :j], axis=1, dtype=self.dt)
+        return np.stack((self.ll[:j] @ np.cos(c).T, self.ll[:j] @ np.sin(c).T))
+
+    def jacobian_joint(self, q, j):                     # d fk_joint_j / d q: reverse cumsum over the first j links
+        c = np.cumsum(q.reshape(-1, 3), axis=1, dtype=self.dt)
+        x = -(self.ll * np.sin(c))
+        y = self.ll * np.cos(c)
+        x[:, j:] = 0
+        y[:, j:] = 0
+        rx = x + np.sum(x, axis=1, dtype=self.dt)[:, None] - np.cumsum(x, axis=1, dtype=self.dt)
+        ry = y + np.sum(y, axis=1, dtype=self.dt)[:, None] - np.cumsum(y, axis=1, dtype=self.dt)
+        rx[:, j:] = 0
+        ry[:, j:] = 0
+        return np.stack((rx, ry))
+
     def _norm(self, x):
         return np.sqrt(np.sum(np.square(x), dtype=self.dt))
 
@@ -269,11 +288,36 @@ class TrajectoryModel:
         return (dt(lam_max) * w_max + (dt(1) - dt(lam_max)) * (np.ones((1, T), dt) / dt(T))) * cg
 
     def obstacle_cost(self, q, obstacles, lam_max):      # trajectory.py:113-117
+        if getattr(self.hp, "whole_arm_cost", False):
+            return self._whole_arm_cost(q, obstacles, lam_max)
         return self.point_cost(self.robot.fk(q), obstacles, lam_max)
 
     def obstacle_cost_g(self, q, obstacles, lam_max):    # trajectory.py:120-126
+        if getattr(self.hp, "whole_arm_cost", False):
+            return self._whole_arm_cost_g(q, obstacles, lam_max)
         cg = self.point_cost_g(self.robot.fk(q), obstacles, lam_max)
         return np.einsum("ij,ijk->jk", cg, self.robot.jacobian(q))
+
+    # whole-arm extension (blog-post.html:505-513): cost_v[t] = sum_j costmap(fk_j(q_t)), then the same
+    # max/mean weighting (trajectory.py:81-110) on the summed per-sample cost
+    def _whole_arm_cost(self, q, obstacles, lam_max):
+        dt = self.dt
+        cv = compute_cost(self.robot.fk_joint(q, 1), obstacles, dt)
+        for j in (2, 3):
+            cv = cv + compute_cost(self.robot.fk_joint(q, j), obstacles, dt)
+        return dt(lam_max) * cv.max() + (dt(1) - dt(lam_max)) * (np.sum(cv, dtype=dt) / dt(cv.shape[0]))
+
+    def _whole_arm_cost_g(self, q, obstacles, lam_max):
+        dt = self.dt
+        parts = [compute_cost_vg(self.robot.fk_joint(q, j), obstacles, dt) for j in (1, 2, 3)]
+        cv = (parts[0][0] + parts[1][0]) + parts[2][0]
+        T = cv.shape[0]
+        w = (dt(1) - dt(lam_max)) * (np.ones((1, T), dt) / dt(T))
+        w[0, int(np.argmax(cv))] += dt(lam_max)
+        g = np.zeros_like(q)
+        for j in (3, 2, 1):
+            g = g + np.einsum("ij,ijk->jk", w * parts[j - 1][1], self.robot.jacobian_joint(q, j))
+        return g
 
     # -- penalties --------------------------------------------------------
     def sg_cost(self, q, start, goal):                   # trajectory.py:183-188

@@ -27,7 +27,7 @@ class MirrorCfg(C.Structure):
                [(n, C.c_float) for n in ("lam_sg0", "lam_jl0", "lam_inc", "lam_max", "lam_reg", "eps_loop", "eps_pos",
                                          "eps_vel", "bls_lr0", "bls_alpha", "bls_bp", "bls_bm", "safety", "qmax", "qmin",
                                          "vmax")] + \
-               [("link", C.c_float * 3), ("J", C.c_float * 9), ("gd_lr", C.c_float * 16)]
+               [("link", C.c_float * 3), ("J", C.c_float * 9), ("gd_lr", C.c_float * 16), ("whole_arm", C.c_int)]
 
 
 def build(force: bool = False) -> str:
@@ -69,6 +69,7 @@ def make_cfg(hp, jac: np.ndarray, n_obs: int, mode: str) -> MirrorCfg:
     c.cvdl = int(bool(hp.constraint_violating_dependant_loss))
     c.mode = {"bls": 0, "gd": 1}[mode]
     c.strict = 1
+    c.whole_arm = int(bool(getattr(hp, "whole_arm_cost", False)))
     c.lam_sg0, c.lam_jl0 = hp.lambda_sg_constraint, hp.lambda_jl_constraint
     c.lam_inc, c.lam_max, c.lam_reg = hp.lambda_constraint_increase, hp.lambda_max_cost, hp.lambda_reg
     c.eps_loop, c.eps_pos, c.eps_vel = hp.loop_loss_reduction, hp.eps_position, hp.eps_velocity

@@ -40,8 +40,8 @@ def test_library_contains_sm100a_code_only():
 
 def test_config_struct_layout_matches_header():
     from irm_motion_planning_b200 import backend
-    # 10 int32 + 16 float + 3 + 9 + 16 floats, then two pointers (8-byte aligned)
-    off = 4 * (10 + 16 + 3 + 9 + 16)
+    # 11 int32 + 16 float + 3 + 9 + 16 floats, then two pointers (8-byte aligned)
+    off = 4 * (11 + 16 + 3 + 9 + 16)
     assert backend.FgdConfig.h_km.offset == (off + 7) // 8 * 8
     assert ctypes.sizeof(backend.FgdConfig) == backend.FgdConfig.h_km.offset + 16
 

@@ -259,6 +259,30 @@ def test_device_init_trajectory_bit_exact_and_optimisable(cuda_ready, T, B):
         assert np.array_equal(is_.cpu().numpy(), cis) and np.array_equal(a.cpu().numpy(), ca)
 
 
+@pytest.mark.parametrize("T,n_obs,mode", [(50, 11, "bls"), (100, 30, "gd"), (256, 64, "bls")])
+def test_whole_arm_cost_bit_exact(cuda_ready, T, n_obs, mode):
+    """obstacle cost over all joint positions (ARM kernels) -- per evaluation and whole
+    optimisations bit-identical to the mirror oracle in strict mode."""
+    over = {"whole_arm_cost": True, "max_inner_iteration": 25, "max_outer_iteration": 2}
+    args, tr, obs, start, goal, alpha0 = _setup(T=T, n_obs=n_obs, B=20, seed=T + 3, **over)
+    m = _mirror(args, tr, obs, mode)
+    assert m.cfg.whole_arm == 1
+    for lam in ((0.5, 0.1), (50.0, 10.0)):
+        g = _gpu_eval(tr, alpha0, start, goal, *lam)
+        c = m.eval(alpha0, start, goal, *lam)
+        for k in ("q", "v", "loss", "toc", "grad"):
+            assert np.array_equal(g[k], c[k]), (k, np.abs(g[k] - c[k]).max())
+    a, fs, is_ = _gpu_optimize(tr, mode, alpha0, start, goal)
+    ca, cfs, cis = m.optimize(alpha0, start, goal)
+    assert np.array_equal(is_.cpu().numpy(), cis)
+    assert np.array_equal(a.cpu().numpy(), ca)
+    # and it is a different objective from the end-effector cost
+    args0, tr0, *_ = _setup(T=T, n_obs=n_obs, B=20, seed=T + 3)
+    tr0.set_obstacles(obs)
+    g0 = _gpu_eval(tr0, alpha0, start, goal, 0.5, 0.1)
+    assert (g["toc"] > g0["toc"]).all()
+
+
 def test_warm_start_replanning_bit_exact(cuda_ready):
     """a stream of scene updates, every plan warm-started from the previous solution through
     the persistent handle (async obstacle upload, no re-creation); the oracle applies the same schedule."""

@@ -197,3 +197,37 @@ def test_rank2_init_reproduces_the_reference_line_fit(T):
     # linearity: the rank-2 form is exactly linear in (start, goal) up to rounding
     a2 = M.init_trajectory(*tr.init_basis(), 2 * s, 2 * g)
     assert np.allclose(a2, 2 * a_rank2, rtol=1e-5, atol=1e-3)
+
+
+def test_whole_arm_cost_extension():
+    """SURVEY 8f-3 / blog-post.html:505-513: obstacle cost summed over the three joint positions.
+    There is no reference implementation, so the NumPy oracle is pinned by (i) fk_joint_3 == fk and its
+    Jacobian == robot.jacobian, (ii) an FP64 finite-difference check of the gradient, and the mirror
+    by the NumPy oracle (loss rel <= 2e-6, gradient rel <= 5e-6)."""
+    hp = O.Hyper(whole_arm_cost=True)
+    tm64 = O.TrajectoryModel(hp, dtype=np.float64)
+    rng = np.random.default_rng(5)
+    alpha = rng.standard_normal((50, 3)) * 0.05
+    s, g = np.array([0.1, -0.2, 0.3]), np.array([1.2, 1.0, 0.3])
+    q = tm64.evaluate(alpha, tm64.km)
+    assert np.array_equal(tm64.robot.fk_joint(q, 3), tm64.robot.fk(q))
+    assert np.array_equal(tm64.robot.jacobian_joint(q, 3), tm64.robot.jacobian(q))
+    f = lambda a: tm64.cost(a, OBS, s, g, 0.5, 0.1, 0.5)
+    G = tm64.cost_g(alpha, OBS, s, g, 0.5, 0.1, 0.5)
+    num = np.zeros_like(alpha)
+    for i in range(50):
+        for j in range(3):
+            e = np.zeros_like(alpha); e[i, j] = 1e-6
+            num[i, j] = (f(alpha + e) - f(alpha - e)) / 2e-6
+    assert _rel(G, num) < 1e-7
+    # the extension changes the objective: three times the potential, roughly
+    assert tm64.obstacle_cost(q, OBS, 0.5) > 2.0 * O.TrajectoryModel(O.Hyper(), dtype=np.float64).obstacle_cost(q, OBS, 0.5)
+    tm32 = O.TrajectoryModel(hp)
+    m = M.Mirror(hp, tm32.km, tm32.dkm, tm32.jac, OBS, "bls")
+    a32 = alpha.astype(np.float32)[None]
+    e = m.eval(a32, s.astype(np.float32), g.astype(np.float32), 0.5, 0.1)
+    np.testing.assert_allclose(e["loss"][0], f(alpha), rtol=2e-6)
+    assert _rel(e["grad"][0], G) < 5e-6
+    # end to end on the default problem: converges, constraints fulfilled
+    a, fs, is_ = m.optimize(tm32.init_trajectory(START, GOAL)[None], START, GOAL)
+    assert is_[0, M.I_STATUS] == M.ST_DONE and is_[0, M.I_FULFILLED] == 1

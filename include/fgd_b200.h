@@ -44,7 +44,8 @@ typedef enum FgdStatus {
     FGD_ERR_INVALID_ARGUMENT = 1,
     FGD_ERR_UNSUPPORTED_T = 2,        /* T < 2 or T > FGD_MAX_T                    */
     FGD_ERR_KERNEL_NOT_SYMMETRIC = 3, /* km != km^T or dkm != -dkm^T bit-wise      */
-    FGD_ERR_TOO_MANY_OBSTACLES = 4,   /* count > obstacle_capacity                 */
+    FGD_ERR_TOO_MANY_OBSTACLES = 4,   /* count > obstacle_capacity, or a capacity whose staging buffer
+                                         does not fit in shared memory (~20 000 obstacles)        */
     FGD_ERR_CUDA = 5,                 /* see fgd_last_cuda_error()                 */
     FGD_ERR_NO_DEVICE = 6,
     FGD_ERR_JOINTS = 7                /* n_joints != 3 (robot.py:31, trajectory.py:42) */

@@ -203,7 +203,7 @@ const char *fgd_status_string(int s)
         case FGD_ERR_INVALID_ARGUMENT: return "invalid argument";
         case FGD_ERR_UNSUPPORTED_T: return "n_timesteps outside [2, 256]";
         case FGD_ERR_KERNEL_NOT_SYMMETRIC: return "km must be symmetric and dkm antisymmetric (bit-wise)";
-        case FGD_ERR_TOO_MANY_OBSTACLES: return "obstacle count exceeds obstacle_capacity";
+        case FGD_ERR_TOO_MANY_OBSTACLES: return "obstacle count exceeds obstacle_capacity (or the capacity does not fit in shared memory)";
         case FGD_ERR_CUDA: return "CUDA error (see fgd_last_cuda_error)";
         case FGD_ERR_NO_DEVICE: return "no CUDA device";
         case FGD_ERR_JOINTS: return "n_joints must be 3";
@@ -248,6 +248,11 @@ int fgd_create(const FgdConfig *cfg, FgdHandle **out)
     // K and dK go to shared memory when both fit beside the operand buffers of at least one slot per warp
     if (const char *e = std::getenv("FGD_VARIANT")) { const int v = std::atoi(e); if (variant_exists(v, h->WPT)) h->variant = v; }
     h->k_in_smem = h->WPT == 1;   // T <= 64: 3*T*64*4 B <= 48 KB per CTA; larger T reads the K tables from L2
+    {   // the whole obstacle set is staged in shared memory next to the K tables and the operand buffers
+        const int nw = warps_per_cta(h->variant, h->WPT);
+        const size_t need = make_layout(T, h->TP, cfg->obstacle_capacity, h->k_in_smem, nw / h->WPT, h->WPT).bytes() + 64;
+        if (need > (size_t)h->max_smem_optin) return fail(FGD_ERR_TOO_MANY_OBSTACLES);
+    }
 
     // operand table KD[k][thread][2R]: the R row entries K[t][k] then the R entries dK[t][k] of the team thread's rows
     // t = R*thread + r, and KO[k][thread][R]: the K entries alone (dense half of the backward contraction)

@@ -348,6 +348,18 @@ def test_edge_cases_and_errors(cuda_ready):
     with pytest.raises(backend.FgdError) as ei:
         tr.handle.set_obstacles(np.zeros((17, 2), np.float32))
     assert ei.value.status == 4
+    # a capacity whose staging buffer cannot fit in shared memory is refused at creation, large-but-fitting ones work
+    from irm_motion_planning_b200.trajectory import Trajectory as _T
+    with pytest.raises(backend.FgdError) as ei:
+        _T(args, obstacle_capacity=200000)
+    assert ei.value.status == 4
+    big = _T(args, obstacle_capacity=8192, strict_math=True)
+    rng = np.random.default_rng(1)
+    many = rng.uniform(-4, 4, (8000, 2)).astype(np.float32)
+    big.set_obstacles(many)
+    gb = {k: v.cpu().numpy() for k, v in big._eval(alpha0, None, start, goal, 0.5, 0.1, -1.0, ("loss", "grad")).items()}
+    cb = _mirror(args, big, many, "bls").eval(alpha0, start, goal, 0.5, 0.1)
+    assert np.array_equal(gb["loss"], cb["loss"]) and np.array_equal(gb["grad"], cb["grad"])
     # already finished trajectories are left untouched by another launch
     tr.set_obstacles(obs)
     a, fs, is_ = _gpu_optimize(tr, "bls", alpha0, start, goal)

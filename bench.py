@@ -319,10 +319,10 @@ def main():
         e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-        h2d = B * T * 12 + 2 * B * 12 + B * (backend.FSTATE + backend.ISTATE) * 4
+        h2d = B * T * 12 + 2 * B * 12
         d2h = B * T * 12 + B * (backend.FSTATE + backend.ISTATE) * 4
         e2e = {"value": n_traj_all * a.steps / float(e2e_s.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "api": "fgd_optimize_host via BatchedFGD.optimize_pinned"}
+               "d2h_bytes_per_step": int(d2h), "api": "fgd_optimize_host_io via BatchedFGD.optimize_pinned"}
 
     if rank != 0:
         if world > 1:

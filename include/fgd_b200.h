@@ -142,6 +142,13 @@ int fgd_optimize_gd(FgdHandle *h, int32_t B, float *d_alpha, const float *d_star
 int fgd_optimize_host(FgdHandle *h, int32_t use_gd, int32_t B, float *h_alpha, const float *h_start,
                       const float *h_goal, float *h_fstate, int32_t *h_istate, void *stream);
 
+/* Fresh run with separate input and output host buffers (the shape of the reference's operator: alpha in,
+ * new alpha out, `main.py:122`): h_alpha_in is only read, the loop state starts from zero on the device
+ * (no state upload) and the final alpha / state are written to the *_out buffers.  Synchronous. */
+int fgd_optimize_host_io(FgdHandle *h, int32_t use_gd, int32_t B, const float *h_alpha_in, float *h_alpha_out,
+                         const float *h_start, const float *h_goal, float *h_fstate_out, int32_t *h_istate_out,
+                         void *stream);
+
 /* Random-restart reduction: trajectories are laid out [n_problems][n_restarts];
  * for each problem pick the restart with the lowest obstacle cost among the
  * constraint-fulfilling ones (falls back to lowest cost if none is fulfilled).

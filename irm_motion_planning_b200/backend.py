@@ -49,7 +49,7 @@ EXPORTED_SYMBOLS = (
     "fgd_create", "fgd_destroy", "fgd_status_string", "fgd_last_cuda_error", "fgd_set_obstacles_async",
     "fgd_obstacle_count", "fgd_eval_cost_grad", "fgd_optimize_bls", "fgd_optimize_gd", "fgd_optimize_host",
     "fgd_argmin_per_problem", "fgd_launch_geometry", "fgd_kernel_launches", "fgd_abi_version",
-    "fgd_measure_fp32_peak", "fgd_set_init_basis", "fgd_init_trajectory",
+    "fgd_measure_fp32_peak", "fgd_set_init_basis", "fgd_init_trajectory", "fgd_optimize_host_io",
 )
 
 _lib = None
@@ -79,6 +79,7 @@ def load_library(path: Optional[str] = None):
     lib.fgd_optimize_bls.argtypes = [vp, i32, fp, fp, fp, fp, ip, i32, vp]
     lib.fgd_optimize_gd.argtypes = [vp, i32, fp, fp, fp, fp, ip, i32, vp]
     lib.fgd_optimize_host.argtypes = [vp, i32, i32, fp, fp, fp, fp, ip, vp]
+    lib.fgd_optimize_host_io.argtypes = [vp, i32, i32, fp, fp, fp, fp, fp, ip, vp]
     lib.fgd_argmin_per_problem.argtypes = [vp, i32, i32, fp, ip, i32, fp, ip, vp]
     lib.fgd_set_init_basis.argtypes = [vp, fp, fp, fp]
     lib.fgd_init_trajectory.argtypes = [vp, i32, fp, fp, fp, vp]
@@ -225,6 +226,11 @@ class Handle:
     def optimize_host(self, mode: str, B, alpha, start, goal, fstate, istate):
         self._check(self._lib.fgd_optimize_host(self._h, 1 if mode == "gd" else 0, B, _ptr(alpha), _ptr(start), _ptr(goal),
                                                 _ptr(fstate), _ptr(istate), self._stream()), "fgd_optimize_host")
+
+    def optimize_host_io(self, mode: str, B, alpha_in, alpha_out, start, goal, fstate_out, istate_out):
+        self._check(self._lib.fgd_optimize_host_io(self._h, 1 if mode == "gd" else 0, B, _ptr(alpha_in), _ptr(alpha_out),
+                                                   _ptr(start), _ptr(goal), _ptr(fstate_out), _ptr(istate_out),
+                                                   self._stream()), "fgd_optimize_host_io")
 
     def argmin_per_problem(self, n_problems, n_restarts, fstate, istate, index_offset, best_cost, best_index):
         self._check(self._lib.fgd_argmin_per_problem(self._h, n_problems, n_restarts, _ptr(fstate), _ptr(istate),

@@ -100,19 +100,16 @@ class BatchedFGD:
         B = alpha.shape[0]
         start = np.ascontiguousarray(np.broadcast_to(np.asarray(start, np.float32).reshape(-1, 3), (B, 3)))
         goal = np.ascontiguousarray(np.broadcast_to(np.asarray(goal, np.float32).reshape(-1, 3), (B, 3)))
-        out = alpha.copy()
-        fs = np.zeros((B, backend.FSTATE), np.float32)
-        is_ = np.zeros((B, backend.ISTATE), np.int32)
-        self.handle.optimize_host(self.mode, B, out, start, goal, fs, is_)
+        out = np.empty_like(alpha)
+        fs = np.empty((B, backend.FSTATE), np.float32)
+        is_ = np.empty((B, backend.ISTATE), np.int32)
+        self.handle.optimize_host_io(self.mode, B, alpha, out, start, goal, fs, is_)
         return BatchResult(out, fs, is_)
 
     def optimize_pinned(self, alpha_pin, start_pin, goal_pin, out_alpha_pin, out_f_pin, out_i_pin) -> None:
         """Same as optimize_host but on caller-owned pinned torch tensors (no allocation in the timed path)."""
         B = int(alpha_pin.shape[0])
-        out_alpha_pin.copy_(alpha_pin)
-        out_f_pin.zero_()
-        out_i_pin.zero_()
-        self.handle.optimize_host(self.mode, B, out_alpha_pin, start_pin, goal_pin, out_f_pin, out_i_pin)
+        self.handle.optimize_host_io(self.mode, B, alpha_pin, out_alpha_pin, start_pin, goal_pin, out_f_pin, out_i_pin)
 
     # -- restart sweep: local argmin + one gather ---------------------------
     def best_per_problem(self, result: BatchResult, n_problems: int, n_restarts: int, index_offset: int = 0):

@@ -190,6 +190,21 @@ int run_optimize(FgdHandle *h, int mode, int B, float *d_alpha, const float *d_s
     return FGD_OK;
 }
 
+int ensure_scratch(FgdHandle *h, int B)
+{
+    if (B > h->s_cap) {
+        cudaFree(h->s_alpha); cudaFree(h->s_start); cudaFree(h->s_goal); cudaFree(h->s_fstate); cudaFree(h->s_istate);
+        h->s_alpha = h->s_start = h->s_goal = h->s_fstate = nullptr; h->s_istate = nullptr; h->s_cap = 0;
+        CK(cudaMalloc(&h->s_alpha, (size_t)B * h->T * 3 * 4));
+        CK(cudaMalloc(&h->s_start, (size_t)B * 3 * 4));
+        CK(cudaMalloc(&h->s_goal, (size_t)B * 3 * 4));
+        CK(cudaMalloc(&h->s_fstate, (size_t)B * FGD_FSTATE * 4));
+        CK(cudaMalloc(&h->s_istate, (size_t)B * FGD_ISTATE * 4));
+        h->s_cap = B;
+    }
+    return FGD_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -389,15 +404,9 @@ int fgd_optimize_host(FgdHandle *h, int32_t use_gd, int32_t B, float *h_alpha, c
     if (!h || B < 0 || (B > 0 && (!h_alpha || !h_start || !h_goal || !h_fstate || !h_istate))) return FGD_ERR_INVALID_ARGUMENT;
     if (B == 0) return FGD_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    if (B > h->s_cap) {
-        cudaFree(h->s_alpha); cudaFree(h->s_start); cudaFree(h->s_goal); cudaFree(h->s_fstate); cudaFree(h->s_istate);
-        h->s_alpha = h->s_start = h->s_goal = h->s_fstate = nullptr; h->s_istate = nullptr; h->s_cap = 0;
-        CK(cudaMalloc(&h->s_alpha, (size_t)B * h->T * 3 * 4));
-        CK(cudaMalloc(&h->s_start, (size_t)B * 3 * 4));
-        CK(cudaMalloc(&h->s_goal, (size_t)B * 3 * 4));
-        CK(cudaMalloc(&h->s_fstate, (size_t)B * FGD_FSTATE * 4));
-        CK(cudaMalloc(&h->s_istate, (size_t)B * FGD_ISTATE * 4));
-        h->s_cap = B;
+    {
+        int rc0 = ensure_scratch(h, B);
+        if (rc0) return rc0;
     }
     CK(cudaMemcpyAsync(h->s_alpha, h_alpha, (size_t)B * h->T * 3 * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->s_start, h_start, (size_t)B * 3 * 4, cudaMemcpyHostToDevice, st));
@@ -409,6 +418,29 @@ int fgd_optimize_host(FgdHandle *h, int32_t use_gd, int32_t B, float *h_alpha, c
     CK(cudaMemcpyAsync(h_alpha, h->s_alpha, (size_t)B * h->T * 3 * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(h_fstate, h->s_fstate, (size_t)B * FGD_FSTATE * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(h_istate, h->s_istate, (size_t)B * FGD_ISTATE * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return FGD_OK;
+}
+
+int fgd_optimize_host_io(FgdHandle *h, int32_t use_gd, int32_t B, const float *h_alpha_in, float *h_alpha_out,
+                         const float *h_start, const float *h_goal, float *h_fstate_out, int32_t *h_istate_out, void *stream)
+{
+    if (!h || B < 0 || (B > 0 && (!h_alpha_in || !h_alpha_out || !h_start || !h_goal || !h_fstate_out || !h_istate_out)))
+        return FGD_ERR_INVALID_ARGUMENT;
+    if (B == 0) return FGD_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = ensure_scratch(h, B);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h->s_alpha, h_alpha_in, (size_t)B * h->T * 3 * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->s_start, h_start, (size_t)B * 3 * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->s_goal, h_goal, (size_t)B * 3 * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(h->s_fstate, 0, (size_t)B * FGD_FSTATE * 4, st));
+    CK(cudaMemsetAsync(h->s_istate, 0, (size_t)B * FGD_ISTATE * 4, st));
+    rc = run_optimize(h, use_gd ? 1 : 0, B, h->s_alpha, h->s_start, h->s_goal, h->s_fstate, h->s_istate, -1, st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h_alpha_out, h->s_alpha, (size_t)B * h->T * 3 * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_fstate_out, h->s_fstate, (size_t)B * FGD_FSTATE * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_istate_out, h->s_istate, (size_t)B * FGD_ISTATE * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return FGD_OK;
 }

@@ -224,6 +224,13 @@ def test_host_buffer_entry_equals_device_path(cuda_ready):
     res = BatchedFGD(tr, "gd").optimize_host(alpha0, start, goal)
     assert np.array_equal(res.alpha, a.cpu().numpy()) and np.array_equal(res.istate, is_.cpu().numpy())
     assert res.done.all()
+    # the in-place entry (resumable state travels with the call) gives the same bits
+    from irm_motion_planning_b200 import backend
+    a2 = alpha0.copy()
+    fs2, is2 = np.zeros((70, backend.FSTATE), np.float32), np.zeros((70, backend.ISTATE), np.int32)
+    tr.handle.optimize_host("gd", 70, a2, start, goal, fs2, is2)
+    assert np.array_equal(a2, res.alpha) and np.array_equal(is2, res.istate) and np.array_equal(fs2, res.fstate)
+    assert np.array_equal(alpha0, _setup(B=70, seed=2)[5])          # optimize_host (io form) left its input untouched
 
 
 def test_result_independent_of_batch_position(cuda_ready):

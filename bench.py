@@ -312,17 +312,22 @@ def main():
         for _ in range(max(1, min(a.warmup, 2))):
             eng.optimize_pinned(a_pin, s_pin, g_pin, out_a, out_f, out_i)
         barrier()
+        zc0 = h.zero_copy_calls()
         t0 = time.perf_counter()
         for _ in range(a.steps):
             eng.optimize_pinned(a_pin, s_pin, g_pin, out_a, out_f, out_i)
         barrier()
+        zero_copy = (h.zero_copy_calls() - zc0) == a.steps
         e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
         h2d = B * T * 12 + 2 * B * 12
         d2h = B * T * 12 + B * (backend.FSTATE + backend.ISTATE) * 4
         e2e = {"value": n_traj_all * a.steps / float(e2e_s.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "api": "fgd_optimize_host_io via BatchedFGD.optimize_pinned"}
+               "d2h_bytes_per_step": int(d2h), "api": "fgd_optimize_host_io via BatchedFGD.optimize_pinned",
+               "transfer": "zero-copy: the kernel reads inputs from / writes results to the pinned host buffers over PCIe, per trajectory"
+                           if zero_copy else "staged: cudaMemcpyAsync H2D, launch, cudaMemcpyAsync D2H"}
+        assert np.array_equal(out_i.numpy()[:, backend.I_STATUS], np.full(B, backend.ST_DONE)), "e2e left unfinished trajectories"
 
     if rank != 0:
         if world > 1:

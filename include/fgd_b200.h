@@ -144,7 +144,11 @@ int fgd_optimize_host(FgdHandle *h, int32_t use_gd, int32_t B, float *h_alpha, c
 
 /* Fresh run with separate input and output host buffers (the shape of the reference's operator: alpha in,
  * new alpha out, `main.py:122`): h_alpha_in is only read, the loop state starts from zero on the device
- * (no state upload) and the final alpha / state are written to the *_out buffers.  Synchronous. */
+ * (no state upload) and the final alpha / state are written to the *_out buffers.  Synchronous.
+ * When all six buffers are page-locked host memory (cudaHostAlloc, cudaHostRegister, torch pin_memory) the call is
+ * ZERO-COPY: the kernel reads each trajectory over PCIe when a team picks it up and writes the result when the team
+ * retires it, so the transfers overlap the optimisation of the other trajectories (fgd_zero_copy_calls counts these
+ * calls).  Pageable buffers take the staged path (H2D copy, launch, D2H copy); the results are identical. */
 int fgd_optimize_host_io(FgdHandle *h, int32_t use_gd, int32_t B, const float *h_alpha_in, float *h_alpha_out,
                          const float *h_start, const float *h_goal, float *h_fstate_out, int32_t *h_istate_out,
                          void *stream);
@@ -175,6 +179,7 @@ int fgd_init_trajectory(FgdHandle *h, int32_t B, const float *d_start, const flo
 int fgd_launch_geometry(const FgdHandle *h, int32_t B, int32_t *grid, int32_t *block, int32_t *smem_bytes,
                         int32_t *warps_per_trajectory);
 int64_t fgd_kernel_launches(const FgdHandle *h);   /* kernels launched through this handle so far */
+int64_t fgd_zero_copy_calls(const FgdHandle *h);   /* fgd_optimize_host_io calls served without staging copies */
 /* FP32 FFMA throughput of the current device (TFLOP/s, best of 5 launches of a
  * pure-FFMA kernel): the measured denominator of the harness's roofline.frac. */
 int fgd_measure_fp32_peak(FgdHandle *h, double *tflops_out, void *stream);

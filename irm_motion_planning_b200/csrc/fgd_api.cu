@@ -26,7 +26,7 @@ struct FgdHandle {
     cudaEvent_t obs_event = nullptr, launch_event = nullptr;
     bool obs_event_pending = false, launch_event_pending = false;
     int last_cuda_error = 0;
-    long long launches = 0;
+    long long launches = 0, zero_copy_calls = 0;
     // scratch for the host-buffer entry point
     float *s_alpha = nullptr, *s_start = nullptr, *s_goal = nullptr, *s_fstate = nullptr;
     int *s_istate = nullptr;
@@ -51,7 +51,8 @@ inline int warps_per_trajectory(int T) { return T <= 64 ? 1 : (T <= 128 ? 2 : 4)
 // per SM (register cap).  Variant 0 is the default; the others exist for tuning (env FGD_VARIANT).
 #define FGD_FOR_CONFIGS(X) \
     X(0, 1, true, 8, 2) X(0, 2, false, 2, 8) X(0, 4, false, 4, 4) \
-    X(1, 1, true, 4, 4) X(1, 2, false, 2, 6) X(1, 4, false, 4, 3)
+    X(1, 1, true, 4, 4) X(1, 2, false, 2, 6) X(1, 4, false, 4, 3) \
+    X(2, 1, true, 10, 2) X(3, 1, true, 12, 2)
 
 template <int WPT, bool STRICT, bool KS, int NW, int MINB, bool ARM>
 cudaError_t launch_opt(const DevParams &p, int grid, size_t smem, cudaStream_t st)
@@ -158,7 +159,8 @@ void fill_params(const FgdHandle *h, DevParams &p, int mode, int B, float *alpha
     p.mode = mode; p.B = B; p.budget = budget;
     p.n_obs = h->obs_count;
     p.obs = h->d_obs[h->obs_active];
-    p.alpha = alpha; p.start = start; p.goal = goal; p.fstate = fstate; p.istate = istate;
+    p.alpha = alpha; p.alpha_in = alpha; p.fresh = 0;
+    p.start = start; p.goal = goal; p.fstate = fstate; p.istate = istate;
     p.queue = h->d_queue;
     p.dbg = h->d_dbg;
 }
@@ -171,8 +173,10 @@ int wait_obstacles(FgdHandle *h, cudaStream_t st)
     return FGD_OK;
 }
 
+// d_alpha_in != nullptr: a fresh run that reads the initial alpha rows from d_alpha_in, writes the results to d_alpha
+// and never reads the loop state (fgd_optimize_host_io).
 int run_optimize(FgdHandle *h, int mode, int B, float *d_alpha, const float *d_start, const float *d_goal, float *d_fstate,
-                 int *d_istate, int budget, cudaStream_t st)
+                 int *d_istate, int budget, cudaStream_t st, const float *d_alpha_in = nullptr)
 {
     if (!h || B < 0 || (B > 0 && (!d_alpha || !d_start || !d_goal || !d_fstate || !d_istate))) return FGD_ERR_INVALID_ARGUMENT;
     if (mode == 1 && h->cfg.max_outer_iteration > h->cfg.n_gd_lr) return FGD_ERR_INVALID_ARGUMENT;   // optimizer_GD.py:34-36
@@ -181,6 +185,7 @@ int run_optimize(FgdHandle *h, int mode, int B, float *d_alpha, const float *d_s
     if (rc) return rc;
     DevParams p;
     fill_params(h, p, mode, B, d_alpha, d_start, d_goal, d_fstate, d_istate, budget);
+    if (d_alpha_in) { p.alpha_in = d_alpha_in; p.fresh = 1; }
     const Geometry g = geometry(h, B, p.n_obs);
     CK(cudaMemsetAsync(h->d_queue, 0, sizeof(unsigned), st));
     CK(dispatch_opt(h->variant, h->WPT, h->cfg.strict_math != 0, h->cfg.whole_arm_cost != 0, p, g.grid, (size_t)g.smem, st));
@@ -188,6 +193,16 @@ int run_optimize(FgdHandle *h, int mode, int B, float *d_alpha, const float *d_s
     CK(cudaEventRecord(h->launch_event, st));
     h->launch_event_pending = true;
     return FGD_OK;
+}
+
+// Page-locked host memory is addressable from the device (unified addressing): returns its device alias.
+bool mapped_host_pointer(const void *p, void **dev)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (at.type != cudaMemoryTypeHost || !at.devicePointer) return false;
+    *dev = at.devicePointer;
+    return true;
 }
 
 int ensure_scratch(FgdHandle *h, int B)
@@ -429,14 +444,32 @@ int fgd_optimize_host_io(FgdHandle *h, int32_t use_gd, int32_t B, const float *h
         return FGD_ERR_INVALID_ARGUMENT;
     if (B == 0) return FGD_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    // Zero-copy: when every buffer is page-locked host memory (cudaHostAlloc / cudaHostRegister / torch pin_memory),
+    // the persistent kernel reads each trajectory straight from the caller's input buffer when a team picks it up and
+    // writes alpha / state straight into the output buffers when the team retires it - PCIe traffic overlaps the
+    // arithmetic of the other teams and there is no staging copy, no memset and no separate D2H pass.
+    // FGD_HOST_IO=copy forces the staged path (A/B measurements).
+    {
+        static const bool force_copy = [] { const char *e = std::getenv("FGD_HOST_IO"); return e && std::strcmp(e, "copy") == 0; }();
+        void *d_in = nullptr, *d_out = nullptr, *d_s = nullptr, *d_g = nullptr, *d_f = nullptr, *d_i = nullptr;
+        if (!force_copy && mapped_host_pointer(h_alpha_in, &d_in) && mapped_host_pointer(h_alpha_out, &d_out) &&
+            mapped_host_pointer(h_start, &d_s) && mapped_host_pointer(h_goal, &d_g) && mapped_host_pointer(h_fstate_out, &d_f) &&
+            mapped_host_pointer(h_istate_out, &d_i)) {
+            int rc = run_optimize(h, use_gd ? 1 : 0, B, (float *)d_out, (const float *)d_s, (const float *)d_g, (float *)d_f, (int *)d_i,
+                                  -1, st, (const float *)d_in);
+            if (rc) return rc;
+            h->zero_copy_calls += 1;
+            CK(cudaStreamSynchronize(st));
+            return FGD_OK;
+        }
+    }
     int rc = ensure_scratch(h, B);
     if (rc) return rc;
     CK(cudaMemcpyAsync(h->s_alpha, h_alpha_in, (size_t)B * h->T * 3 * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->s_start, h_start, (size_t)B * 3 * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->s_goal, h_goal, (size_t)B * 3 * 4, cudaMemcpyHostToDevice, st));
-    CK(cudaMemsetAsync(h->s_fstate, 0, (size_t)B * FGD_FSTATE * 4, st));
-    CK(cudaMemsetAsync(h->s_istate, 0, (size_t)B * FGD_ISTATE * 4, st));
-    rc = run_optimize(h, use_gd ? 1 : 0, B, h->s_alpha, h->s_start, h->s_goal, h->s_fstate, h->s_istate, -1, st);
+    // the loop state is write-only for a fresh run (DevParams::fresh): no memset, no upload
+    rc = run_optimize(h, use_gd ? 1 : 0, B, h->s_alpha, h->s_start, h->s_goal, h->s_fstate, h->s_istate, -1, st, h->s_alpha);
     if (rc) return rc;
     CK(cudaMemcpyAsync(h_alpha_out, h->s_alpha, (size_t)B * h->T * 3 * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(h_fstate_out, h->s_fstate, (size_t)B * FGD_FSTATE * 4, cudaMemcpyDeviceToHost, st));
@@ -497,6 +530,7 @@ int fgd_launch_geometry(const FgdHandle *h, int32_t B, int32_t *grid, int32_t *b
 }
 
 int64_t fgd_kernel_launches(const FgdHandle *h) { return h ? h->launches : 0; }
+int64_t fgd_zero_copy_calls(const FgdHandle *h) { return h ? h->zero_copy_calls : 0; }
 
 #if defined(FGD_DEBUG_MARK) || defined(FGD_PHASE_CLOCKS)
 int *fgd_debug_buffer(FgdHandle *h) { return h->h_dbg; }

@@ -46,7 +46,9 @@ struct DevParams {
     const float *KD;         // [T][TP/2][4]: K[t][k], K[t+1][k], dK[t][k], dK[t+1][k] of team thread t/2 (zero padded rows >= T)
     const float *KO;         // [T][TP/2][2]: K entries only (dense half of the backward contraction)
     const float *obs;        // [n_obs][2]
-    float *alpha;            // [B][T][3]
+    float *alpha;            // [B][T][3]  final alpha rows are written here
+    const float *alpha_in;   // [B][T][3]  initial alpha rows are read from here (== alpha for the in-place calls)
+    int fresh;               // 1: every trajectory starts from the zero loop state (istate / fstate are write-only)
     const float *start, *goal;
     float *fstate;
     int *istate;

@@ -65,28 +65,39 @@ __device__ __forceinline__ void make_candidate(const DevParams &p, float lr, con
     for (int b = 0; b < 3; ++b) c[b] = fma2(bc2(c1), a[b], neg2(mul2(bc2(lr), d[b])));
 }
 
+// Trajectory I/O goes through the team's operand buffer XA viewed as 3T packed floats ("stage"), so that global
+// memory only sees linear, fully coalesced 128 B accesses.  That matters most for the zero-copy host path
+// (fgd_optimize_host_io on pinned buffers): p.alpha_in / p.alpha / p.start / p.goal / p.fstate / p.istate are then
+// mapped HOST pointers and every access is a PCIe transaction - the kernel pulls a trajectory when a team picks it
+// up and pushes the result when the team retires it, overlapped with the other teams' arithmetic.
 template <int WPT>
-__device__ __forceinline__ void save_slot(const DevParams &p, const Team<WPT> &G, const Slot &st, int status, const f2 (&a)[3])
+__device__ __forceinline__ void save_slot(const DevParams &p, const Team<WPT> &G, const Slot &st, int status, const f2 (&a)[3], float *stage)
 {
     const int b = st.traj;
-    float *ap = p.alpha + (size_t)b * p.T * 3;
     const int t = G.tl * R;
-    if (t < p.T) { ap[t * 3] = a[0].x; ap[t * 3 + 1] = a[1].x; ap[t * 3 + 2] = a[2].x; }
-    if (t + 1 < p.T) { ap[t * 3 + 3] = a[0].y; ap[t * 3 + 4] = a[1].y; ap[t * 3 + 5] = a[2].y; }
-    if (G.tl == 0) {
-        float *fs = p.fstate + (size_t)b * FGD_FSTATE;
-        int *is = p.istate + (size_t)b * FGD_ISTATE;
-        fs[FGD_F_LAM_SG] = st.lam_sg; fs[FGD_F_LAM_JL] = st.lam_jl; fs[FGD_F_LR] = st.lr;
-        fs[FGD_F_LOSS] = st.loss; fs[FGD_F_TOC] = st.toc; fs[FGD_F_LAST_NEW_LOSS] = st.last_new;
-        is[FGD_I_STATUS] = status; is[FGD_I_OUTER] = st.outer; is[FGD_I_INNER] = st.inner;
-        is[FGD_I_INNER_TOTAL] = st.inner_total; is[FGD_I_CAND_EVALS] = st.cand_evals; is[FGD_I_ACCEPTS] = st.accepts;
-        is[FGD_I_FULFILLED] = st.ful; is[FGD_I_HASH] = (int)st.hash;
+    G.sync();                                         // the team is done with whatever XA held
+    if (t < p.T) { stage[t * 3] = a[0].x; stage[t * 3 + 1] = a[1].x; stage[t * 3 + 2] = a[2].x; }
+    if (t + 1 < p.T) { stage[t * 3 + 3] = a[0].y; stage[t * 3 + 4] = a[1].y; stage[t * 3 + 5] = a[2].y; }
+    G.sync();
+    float *ap = p.alpha + (size_t)b * p.T * 3;
+    const int n = p.T * 3;
+    for (int i = G.tl; i < n; i += WPT * 32) ap[i] = stage[i];
+    if (G.tl < FGD_FSTATE) {                          // one 32 B row of float state, one of integer state
+        const int i = G.tl;
+        const float fv = i == FGD_F_LAM_SG ? st.lam_sg : i == FGD_F_LAM_JL ? st.lam_jl : i == FGD_F_LR ? st.lr
+                       : i == FGD_F_LOSS ? st.loss : i == FGD_F_TOC ? st.toc : i == FGD_F_LAST_NEW_LOSS ? st.last_new : 0.0f;
+        const int iv = i == FGD_I_STATUS ? status : i == FGD_I_OUTER ? st.outer : i == FGD_I_INNER ? st.inner
+                     : i == FGD_I_INNER_TOTAL ? st.inner_total : i == FGD_I_CAND_EVALS ? st.cand_evals
+                     : i == FGD_I_ACCEPTS ? st.accepts : i == FGD_I_FULFILLED ? st.ful : (int)st.hash;
+        p.fstate[(size_t)b * FGD_FSTATE + i] = fv;
+        p.istate[(size_t)b * FGD_ISTATE + i] = iv;
     }
+    G.sync();                                         // stage is free again
 }
 
 // Pull the next unfinished trajectory from the batch queue (team-uniform).
 template <int WPT>
-__device__ __forceinline__ void fetch_slot(const DevParams &p, const Team<WPT> &G, Slot &st, int &kind, f2 (&a)[3])
+__device__ __forceinline__ void fetch_slot(const DevParams &p, const Team<WPT> &G, Slot &st, int &kind, f2 (&a)[3], float *stage)
 {
     for (;;) {
         unsigned idx = 0;
@@ -102,7 +113,7 @@ __device__ __forceinline__ void fetch_slot(const DevParams &p, const Team<WPT> &
         }
         if (idx >= (unsigned)p.B) { st.traj = -1; kind = K_IDLE; return; }
         const int *is = p.istate + (size_t)idx * FGD_ISTATE;
-        const int status = is[FGD_I_STATUS];
+        const int status = p.fresh ? FGD_ST_FRESH : is[FGD_I_STATUS];
         if (status == FGD_ST_DONE) continue;          // finished in an earlier launch, take the next one
         const float *fs = p.fstate + (size_t)idx * FGD_FSTATE;
         st.traj = (int)idx;
@@ -121,11 +132,15 @@ __device__ __forceinline__ void fetch_slot(const DevParams &p, const Team<WPT> &
         }
 #pragma unroll
         for (int b = 0; b < 3; ++b) { st.start[b] = p.start[(size_t)idx * 3 + b]; st.goal[b] = p.goal[(size_t)idx * 3 + b]; }
-        const float *ap = p.alpha + (size_t)idx * p.T * 3;
+        const float *ap = p.alpha_in + (size_t)idx * p.T * 3;
+        const int n = p.T * 3;
+        for (int i = G.tl; i < n; i += WPT * 32) stage[i] = ap[i];
+        G.sync();
         const int t = G.tl * R;
         const bool ok = t < p.T, ok1 = t + 1 < p.T;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) a[c] = mk2(ok ? ap[t * 3 + c] : 0.0f, ok1 ? ap[t * 3 + 3 + c] : 0.0f);
+        for (int c = 0; c < 3; ++c) a[c] = mk2(ok ? stage[t * 3 + c] : 0.0f, ok1 ? stage[t * 3 + 3 + c] : 0.0f);
+        G.sync();                                     // rows are in registers: the caller may overwrite XA
         kind = K_EVAL0;
         return;
     }
@@ -333,8 +348,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
             }
         }
         if (retire || save_active || boot) {
-            if (!boot) save_slot<WPT>(p, G, st, retire ? FGD_ST_DONE : FGD_ST_ACTIVE, a);
-            fetch_slot<WPT>(p, G, st, kind, a);
+            if (!boot) save_slot<WPT>(p, G, st, retire ? FGD_ST_DONE : FGD_ST_ACTIVE, a, reinterpret_cast<float *>(XA));
+            fetch_slot<WPT>(p, G, st, kind, a, reinterpret_cast<float *>(XA));
             want_eval = (kind != K_IDLE);
         }
         if (want_eval) {

@@ -233,6 +233,35 @@ def test_host_buffer_entry_equals_device_path(cuda_ready):
     assert np.array_equal(alpha0, _setup(B=70, seed=2)[5])          # optimize_host (io form) left its input untouched
 
 
+@pytest.mark.parametrize("mode,T,n_obs,B", [("gd", 50, 11, 300), ("bls", 50, 11, 257), ("bls", 129, 20, 40), ("bls", 256, 64, 9)])
+def test_zero_copy_host_io_equals_device_path(cuda_ready, mode, T, n_obs, B):
+    """fgd_optimize_host_io on page-locked buffers: the kernel reads its inputs from and writes its results to HOST
+    memory directly (no staging copies).  Same bits as the device-resident path and as the oracle; pageable buffers
+    take the staged path and give the same bits again."""
+    import torch
+    from irm_motion_planning_b200 import backend
+    from irm_motion_planning_b200.batch import BatchedFGD
+    args, tr, obs, start, goal, alpha0 = _setup(T=T, n_obs=n_obs, B=B, seed=5)
+    a, fs, is_ = _gpu_optimize(tr, mode, alpha0, start, goal)
+    eng = BatchedFGD(tr, mode)
+    pin = lambda x: torch.as_tensor(x).clone().pin_memory()
+    a_in, s_pin, g_pin = pin(alpha0), pin(start), pin(goal)
+    out_a = torch.full((B, T, 3), float("nan")).pin_memory()
+    out_f = torch.full((B, backend.FSTATE), float("nan")).pin_memory()
+    out_i = torch.full((B, backend.ISTATE), -7, dtype=torch.int32).pin_memory()
+    z0, l0 = tr.handle.zero_copy_calls(), tr.handle.kernel_launches()
+    eng.optimize_pinned(a_in, s_pin, g_pin, out_a, out_f, out_i)
+    assert tr.handle.zero_copy_calls() == z0 + 1 and tr.handle.kernel_launches() == l0 + 1
+    assert np.array_equal(out_a.numpy(), a.cpu().numpy())
+    assert np.array_equal(out_i.numpy(), is_.cpu().numpy()) and np.array_equal(out_f.numpy(), fs.cpu().numpy())
+    assert np.array_equal(a_in.numpy(), alpha0)                      # the input buffer is only read
+    ca, cfs, cis = _mirror(args, tr, obs, mode).optimize(alpha0, start, goal)
+    assert np.array_equal(out_a.numpy(), ca) and np.array_equal(out_i.numpy(), cis)
+    res = eng.optimize_host(alpha0, start, goal)                      # pageable NumPy buffers: staged copies
+    assert tr.handle.zero_copy_calls() == z0 + 1
+    assert np.array_equal(res.alpha, ca) and np.array_equal(res.istate, cis) and np.array_equal(res.fstate, out_f.numpy())
+
+
 def test_result_independent_of_batch_position(cuda_ready):
     """Batch-vs-loop consistency: a trajectory's result does not depend on where it sits in the
     batch, which trajectory shares its warp, or the batch size (fast-math mode, the product default)."""

@@ -15,7 +15,6 @@ struct FgdHandle {
     FgdConfig cfg;
     DevParams base;            // everything except the per-call batch pointers
     int T, TP, WPT, variant = 0;
-    bool k_in_smem;
     int device, num_sms, max_smem_optin;
     float *d_KD = nullptr, *d_KO = nullptr;
     float *d_init = nullptr;   // [2T + 9]: u = K^-1 1, w = K^-1 c, J^-1 (fgd_set_init_basis)
@@ -46,35 +45,42 @@ struct Geometry { int grid, block, smem; };
 // warps per trajectory by trajectory length (each thread owns R = 2 adjacent time samples: TP = 64 * WPT >= T)
 inline int warps_per_trajectory(int T) { return T <= 64 ? 1 : (T <= 128 ? 2 : 4); }
 
-// (variant, WPT, KS, NW, MINB): the instantiated kernels.  WPT warps per trajectory; KS: K tables staged in
-// shared memory (T <= 64) or read from L2; NW warps per CTA (= WPT for multi-warp teams), MINB = min CTAs
-// per SM (register cap).  Variant 0 is the default; the others exist for tuning (env FGD_VARIANT).
+// (variant, WPT, KSRC, NW, MINB): the instantiated optimiser kernels.  WPT warps per trajectory; KSRC: where the K tables
+// live - tensor memory (K_TMEM, T <= 64), shared memory (K_SMEM, T <= 64) or L2 (K_L2); NW warps per CTA (= WPT for
+// multi-warp teams), MINB = min CTAs per SM (register cap).  Variant 0 is the default; variant 1 exists for A/B
+// measurements (env FGD_VARIANT): the shared-memory tables for T <= 64, other register caps for the team kernels.
 #define FGD_FOR_CONFIGS(X) \
-    X(0, 1, true, 8, 2) X(0, 2, false, 2, 8) X(0, 4, false, 4, 4) \
-    X(1, 1, true, 4, 4) X(1, 2, false, 2, 6) X(1, 4, false, 4, 3) \
-    X(2, 1, true, 10, 2) X(3, 1, true, 12, 2)
+    X(0, 1, K_TMEM, 16, 1) X(0, 2, K_L2, 2, 8) X(0, 4, K_L2, 4, 4) \
+    X(1, 1, K_SMEM, 8, 2) X(1, 2, K_L2, 2, 6) X(1, 4, K_L2, 4, 3) \
+    X(2, 1, K_TMEM, 8, 2)
+// (WPT, KSRC, NW): the evaluation kernels (parity hook; tables in shared memory / L2)
+#define FGD_FOR_EVAL_CONFIGS(X) X(1, K_SMEM, 8) X(2, K_L2, 2) X(4, K_L2, 4)
 
-template <int WPT, bool STRICT, bool KS, int NW, int MINB, bool ARM>
+template <int WPT, bool STRICT, int KS, int NW, int MINB, bool ARM, int TC = 0>
 cudaError_t launch_opt(const DevParams &p, int grid, size_t smem, cudaStream_t st)
 {
-    auto kern = fgd_optimize_kernel<WPT, STRICT, KS, NW, MINB, ARM>;
+    auto kern = fgd_optimize_kernel<WPT, STRICT, KS, NW, MINB, ARM, TC>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, NW * 32, smem, st>>>(p);
     return cudaGetLastError();
 }
 
-template <int WPT, bool STRICT, bool KS, int NW, int MINB, bool ARM>
+template <int WPT, bool STRICT, int KS, int NW, int MINB, bool ARM, int TC = 0>
 int occupancy_opt(size_t smem)
 {
-    auto kern = fgd_optimize_kernel<WPT, STRICT, KS, NW, MINB, ARM>;
+    auto kern = fgd_optimize_kernel<WPT, STRICT, KS, NW, MINB, ARM, TC>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int nb = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, NW * 32, smem) != cudaSuccess) nb = 1;
+    // kernels that allocate tensor memory: the occupancy calculator assumes one CTA per SM (it cannot know how many of
+    // the 512 columns a CTA takes); each CTA takes TMEM_COLS = 256, so MINB = 2 CTAs fit
+    if (KS == K_TMEM && nb < MINB) nb = MINB;
+    if (const char *e = std::getenv("FGD_OCC")) { const int v = std::atoi(e); if (v > 0) nb = v; }
     return nb < 1 ? 1 : nb;
 }
 
-template <int WPT, bool STRICT, bool KS, int NW, bool ARM>
+template <int WPT, bool STRICT, int KS, int NW, bool ARM>
 cudaError_t launch_eval(const DevParams &p, const EvalPtrs &e, int grid, size_t smem, cudaStream_t st)
 {
     auto kern = fgd_eval_kernel<WPT, STRICT, KS, NW, ARM>;
@@ -92,6 +98,30 @@ bool variant_exists(int v, int WPT)
     return false;
 }
 
+int k_source(int v, int WPT)
+{
+#define X(V_, W_, KS_, NW_, MB_) if (v == V_ && WPT == W_) return KS_;
+    FGD_FOR_CONFIGS(X)
+#undef X
+    return K_L2;
+}
+
+int eval_k_source(int WPT)
+{
+#define X(W_, KS_, NW_) if (WPT == W_) return KS_;
+    FGD_FOR_EVAL_CONFIGS(X)
+#undef X
+    return K_L2;
+}
+
+int eval_warps_per_cta(int WPT)
+{
+#define X(W_, KS_, NW_) if (WPT == W_) return NW_;
+    FGD_FOR_EVAL_CONFIGS(X)
+#undef X
+    return WPT;
+}
+
 int warps_per_cta(int v, int WPT)
 {
 #define X(V_, W_, KS_, NW_, MB_) if (v == V_ && WPT == W_) return NW_;
@@ -100,8 +130,21 @@ int warps_per_cta(int v, int WPT)
     return WPT;
 }
 
+// The default single-warp kernel has an instance specialised for the reference's default T (main.py: --n-timesteps 50).
+constexpr int FGD_TC = 50;
+inline bool use_tc(int v, int WPT, int T)
+{
+    static const bool off = [] { const char *e = std::getenv("FGD_NO_TC"); return e && e[0] == '1'; }();
+    return !off && v == 0 && WPT == 1 && T == FGD_TC;
+}
+
 cudaError_t dispatch_opt(int v, int WPT, bool strict, bool arm, const DevParams &p, int grid, size_t smem, cudaStream_t st)
 {
+    if (use_tc(v, WPT, p.T))
+        return arm ? (strict ? launch_opt<1, true, K_TMEM, 16, 1, true, FGD_TC>(p, grid, smem, st)
+                             : launch_opt<1, false, K_TMEM, 16, 1, true, FGD_TC>(p, grid, smem, st))
+                   : (strict ? launch_opt<1, true, K_TMEM, 16, 1, false, FGD_TC>(p, grid, smem, st)
+                             : launch_opt<1, false, K_TMEM, 16, 1, false, FGD_TC>(p, grid, smem, st));
 #define X(V_, W_, KS_, NW_, MB_)                                                        \
     if (v == V_ && WPT == W_)                                                            \
         return arm ? (strict ? launch_opt<W_, true, KS_, NW_, MB_, true>(p, grid, smem, st)      \
@@ -113,8 +156,11 @@ cudaError_t dispatch_opt(int v, int WPT, bool strict, bool arm, const DevParams 
     return cudaErrorInvalidValue;
 }
 
-int dispatch_occ(int v, int WPT, bool strict, bool arm, size_t smem)
+int dispatch_occ(int v, int WPT, int T, bool strict, bool arm, size_t smem)
 {
+    if (use_tc(v, WPT, T))
+        return arm ? (strict ? occupancy_opt<1, true, K_TMEM, 16, 1, true, FGD_TC>(smem) : occupancy_opt<1, false, K_TMEM, 16, 1, true, FGD_TC>(smem))
+                   : (strict ? occupancy_opt<1, true, K_TMEM, 16, 1, false, FGD_TC>(smem) : occupancy_opt<1, false, K_TMEM, 16, 1, false, FGD_TC>(smem));
 #define X(V_, W_, KS_, NW_, MB_)                                                        \
     if (v == V_ && WPT == W_)                                                            \
         return arm ? (strict ? occupancy_opt<W_, true, KS_, NW_, MB_, true>(smem) : occupancy_opt<W_, false, KS_, NW_, MB_, true>(smem))   \
@@ -126,13 +172,13 @@ int dispatch_occ(int v, int WPT, bool strict, bool arm, size_t smem)
 
 cudaError_t dispatch_eval(int WPT, bool strict, bool arm, const DevParams &p, const EvalPtrs &e, int grid, size_t smem, cudaStream_t st)
 {
-#define X(V_, W_, KS_, NW_, MB_)                                                        \
-    if (V_ == 0 && WPT == W_)                                                            \
+#define X(W_, KS_, NW_)                                                                 \
+    if (WPT == W_)                                                                       \
         return arm ? (strict ? launch_eval<W_, true, KS_, NW_, true>(p, e, grid, smem, st)       \
                              : launch_eval<W_, false, KS_, NW_, true>(p, e, grid, smem, st))     \
                    : (strict ? launch_eval<W_, true, KS_, NW_, false>(p, e, grid, smem, st)      \
                              : launch_eval<W_, false, KS_, NW_, false>(p, e, grid, smem, st));
-    FGD_FOR_CONFIGS(X)
+    FGD_FOR_EVAL_CONFIGS(X)
 #undef X
     return cudaErrorInvalidValue;
 }
@@ -143,8 +189,8 @@ Geometry geometry(const FgdHandle *h, int B, int n_obs)
     const int nw = warps_per_cta(h->variant, h->WPT);
     const int teams = nw / h->WPT;
     g.block = nw * 32;
-    g.smem = (int)make_layout(h->T, h->TP, n_obs, h->k_in_smem, teams, h->WPT).bytes();
-    const int occ = dispatch_occ(h->variant, h->WPT, h->cfg.strict_math != 0, h->cfg.whole_arm_cost != 0, (size_t)g.smem);
+    g.smem = (int)make_layout(h->T, h->TP, n_obs, k_source(h->variant, h->WPT), teams, h->WPT).bytes();
+    const int occ = dispatch_occ(h->variant, h->WPT, h->T, h->cfg.strict_math != 0, h->cfg.whole_arm_cost != 0, (size_t)g.smem);
     const long long need = ((long long)B + teams - 1) / teams;
     const long long cap = (long long)occ * h->num_sms;
     g.grid = (int)(need < cap ? need : cap);
@@ -277,11 +323,12 @@ int fgd_create(const FgdConfig *cfg, FgdHandle **out)
     CKC(cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
     // K and dK go to shared memory when both fit beside the operand buffers of at least one slot per warp
     if (const char *e = std::getenv("FGD_VARIANT")) { const int v = std::atoi(e); if (variant_exists(v, h->WPT)) h->variant = v; }
-    h->k_in_smem = h->WPT == 1;   // T <= 64: 3*T*64*4 B <= 48 KB per CTA; larger T reads the K tables from L2
-    {   // the whole obstacle set is staged in shared memory next to the K tables and the operand buffers
-        const int nw = warps_per_cta(h->variant, h->WPT);
-        const size_t need = make_layout(T, h->TP, cfg->obstacle_capacity, h->k_in_smem, nw / h->WPT, h->WPT).bytes() + 64;
-        if (need > (size_t)h->max_smem_optin) return fail(FGD_ERR_TOO_MANY_OBSTACLES);
+    {   // the whole obstacle set is staged in shared memory next to the operand buffers (and, for the kernels that keep
+        // them there, the K tables): the capacity must fit both the optimiser and the evaluation kernel
+        const int nw = warps_per_cta(h->variant, h->WPT), nwe = eval_warps_per_cta(h->WPT);
+        const size_t need = make_layout(T, h->TP, cfg->obstacle_capacity, k_source(h->variant, h->WPT), nw / h->WPT, h->WPT).bytes() + 64;
+        const size_t need_e = make_layout(T, h->TP, cfg->obstacle_capacity, eval_k_source(h->WPT), nwe / h->WPT, h->WPT).bytes() + 64;
+        if (need > (size_t)h->max_smem_optin || need_e > (size_t)h->max_smem_optin) return fail(FGD_ERR_TOO_MANY_OBSTACLES);
     }
 
     // operand table KD[k][thread][2R]: the R row entries K[t][k] then the R entries dK[t][k] of the team thread's rows
@@ -392,8 +439,8 @@ int fgd_eval_cost_grad(FgdHandle *h, int32_t B, const float *d_alpha, const floa
         p.lam_max = lambda_max_cost; p.oml = 1.0f - p.lam_max; p.w_avg = p.oml * p.inv_T;
     }
     EvalPtrs e{lambda_sg, lambda_jl, d_loss, d_toc, d_grad, d_q, d_v, d_fulfilled};
-    const int nw = warps_per_cta(0, h->WPT), per_cta = nw / h->WPT;
-    const size_t smem = make_layout(h->T, h->TP, p.n_obs, h->k_in_smem, per_cta, h->WPT).bytes();
+    const int nw = eval_warps_per_cta(h->WPT), per_cta = nw / h->WPT;
+    const size_t smem = make_layout(h->T, h->TP, p.n_obs, eval_k_source(h->WPT), per_cta, h->WPT).bytes();
     long long need = ((long long)B + per_cta - 1) / per_cta, cap = (long long)h->num_sms * 4;
     const int grid = (int)(need < cap ? need : cap);
     CK(dispatch_eval(h->WPT, h->cfg.strict_math != 0, h->cfg.whole_arm_cost != 0, p, e, grid, smem, st));

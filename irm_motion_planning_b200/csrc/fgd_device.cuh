@@ -211,6 +211,159 @@ __device__ __forceinline__ void sincos_cw2(f2 x, f2 &S, f2 &C)
     quadrant(j.y, sn.y, cs.y, S.y, C.y);
 }
 
+// where a kernel instance keeps the K / dK operand tables
+enum KSource : int { K_L2 = 0, K_SMEM = 1, K_TMEM = 2 };
+
+// ---------------------------------------------------------------------------
+// Tensor memory (TMEM, 128 lanes x 512 columns x 32 bit per SM) as a per-lane table store (T <= 64,
+// single-warp teams).  Thread `lane` of every warp needs, per column k of the contraction, its own four
+// table entries KD[k][lane] = { K[2l][k], K[2l+1][k], dK[2l][k], dK[2l+1][k] }.  From shared memory that is a
+// 512 B LDS.128 per warp and k - measured ~6 data-pipe cycles - and the shared-memory pipe was the busiest unit
+// of the kernel (75 % of peak, ncu).  TMEM lane l / column 4k..4k+3 holds the same four words: one
+// tcgen05.ld.32x32b (SASS LDTM) hands every thread its entries through the tensor-memory datapath, which is not
+// the shared-memory pipe, sustains > 700 B/cycle/SM (scratch/probe_tmem.cu) and has a 12-cycle latency.  The
+// table is written once per CTA with tcgen05.st; warp w reads the lane quadrant 32 (w % 4), so warps w and
+// w + 4 share one copy.  No tensor-core instruction is involved: the arithmetic stays FP32 FFMA2.
+// The registers of a tcgen05.ld are only valid after tcgen05.wait::ld; the wait takes them as in/out operands
+// so that the compiler cannot move a consumer above it.
+// ---------------------------------------------------------------------------
+constexpr int TMEM_COLS = 256;        // 4 columns per k, T <= 64; two resident CTAs per SM own all 512 columns
+
+__device__ __forceinline__ void tmem_ld16(unsigned ta, unsigned (&r)[16])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(ta));
+}
+__device__ __forceinline__ void tmem_wait16(unsigned (&r)[16])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+                   "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]) :: "memory");
+}
+__device__ __forceinline__ void tmem_ld4(unsigned ta, unsigned (&r)[4])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(ta));
+}
+__device__ __forceinline__ void tmem_wait4(unsigned (&r)[4])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]) :: "memory");
+}
+__device__ __forceinline__ void tmem_ld2(unsigned ta, unsigned (&r)[2])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(ta));
+}
+__device__ __forceinline__ void tmem_wait2(unsigned (&r)[2])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r[0]), "+r"(r[1]) :: "memory");
+}
+__device__ __forceinline__ f2 u2f2(unsigned a, unsigned b) { return make_float2(__uint_as_float(a), __uint_as_float(b)); }
+
+// Forward contraction with the operand table in TMEM: same terms, same order (k ascending, one fma per term) as
+// contract<>.  tk = TMEM address of this warp's lane quadrant, column 0.
+// TC > 0: T is the compile-time constant TC and the loops are fully unrolled (immediate TMEM columns and operand offsets,
+// no loop bookkeeping); TC = 0: runtime T.
+template <bool SAME, int TC>
+__device__ __forceinline__ void contract_tm(unsigned tk, int T, const float4 *__restrict__ x1, const float4 *__restrict__ x2,
+                                            f2 (&y1)[3], f2 (&y2)[3])
+{
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { y1[a] = bc2(0.0f); y2[a] = bc2(0.0f); }
+    int k = 0;
+#pragma unroll (TC > 0 ? 64 : 1)
+    for (; k + 4 <= T; k += 4) {
+        unsigned r[16];
+        tmem_ld16(tk + 4 * k, r);
+        float4 xa[4], xb[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { xa[u] = x1[k + u]; xb[u] = xa[u]; if constexpr (!SAME) xb[u] = x2[k + u]; }
+        tmem_wait16(r);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const f2 kk = u2f2(r[4 * u], r[4 * u + 1]), dk = u2f2(r[4 * u + 2], r[4 * u + 3]);
+            y1[0] = fma2(kk, bc2(xa[u].x), y1[0]);
+            y1[1] = fma2(kk, bc2(xa[u].y), y1[1]);
+            y1[2] = fma2(kk, bc2(xa[u].z), y1[2]);
+            y2[0] = fma2(dk, bc2(xb[u].x), y2[0]);
+            y2[1] = fma2(dk, bc2(xb[u].y), y2[1]);
+            y2[2] = fma2(dk, bc2(xb[u].z), y2[2]);
+        }
+    }
+#pragma unroll (TC > 0 ? 4 : 1)
+    for (; k < T; ++k) {
+        unsigned r[4];
+        tmem_ld4(tk + 4 * k, r);
+        const float4 xa = x1[k];
+        float4 xb = xa;
+        if constexpr (!SAME) xb = x2[k];
+        tmem_wait4(r);
+        const f2 kk = u2f2(r[0], r[1]), dk = u2f2(r[2], r[3]);
+        y1[0] = fma2(kk, bc2(xa.x), y1[0]);
+        y1[1] = fma2(kk, bc2(xa.y), y1[1]);
+        y1[2] = fma2(kk, bc2(xa.z), y1[2]);
+        y2[0] = fma2(dk, bc2(xb.x), y2[0]);
+        y2[1] = fma2(dk, bc2(xb.y), y2[1]);
+        y2[2] = fma2(dk, bc2(xb.z), y2[2]);
+    }
+}
+
+// Backward contraction with the operand table in TMEM (see contract_back<>): K G_q dense, dK (-G_v) over the
+// flagged rows only, both in ascending k.  Single-warp teams.
+template <int TC>
+__device__ __forceinline__ void contract_back_tm(unsigned tk, int T, const float4 *__restrict__ xa_rows, const float4 *__restrict__ xb_rows,
+                                                 const unsigned (&nz)[1][R], f2 (&y1)[3], f2 (&y2)[3])
+{
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { y1[a] = bc2(0.0f); y2[a] = bc2(0.0f); }
+    int k = 0;
+#pragma unroll (TC > 0 ? 64 : 1)
+    for (; k + 4 <= T; k += 4) {
+        unsigned r[16];
+        tmem_ld16(tk + 4 * k, r);
+        float4 xa[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) xa[u] = xa_rows[k + u];
+        tmem_wait16(r);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const f2 kk = u2f2(r[4 * u], r[4 * u + 1]);
+            y1[0] = fma2(kk, bc2(xa[u].x), y1[0]);
+            y1[1] = fma2(kk, bc2(xa[u].y), y1[1]);
+            y1[2] = fma2(kk, bc2(xa[u].z), y1[2]);
+        }
+    }
+#pragma unroll (TC > 0 ? 4 : 1)
+    for (; k < T; ++k) {
+        unsigned r[2];
+        tmem_ld2(tk + 4 * k, r);
+        const float4 xa = xa_rows[k];
+        tmem_wait2(r);
+        const f2 kk = u2f2(r[0], r[1]);
+        y1[0] = fma2(kk, bc2(xa.x), y1[0]);
+        y1[1] = fma2(kk, bc2(xa.y), y1[1]);
+        y1[2] = fma2(kk, bc2(xa.z), y1[2]);
+    }
+    unsigned any = nz[0][0] | nz[0][1];
+    while (any) {                                   // warp-uniform: ascending lane, then ascending r = ascending k
+        const int l = __ffs(any) - 1;
+        any &= any - 1;
+#pragma unroll
+        for (int r_ = 0; r_ < R; ++r_) {
+            if ((nz[0][r_] >> l) & 1u) {
+                const int kz = l * R + r_;
+                unsigned r[2];
+                tmem_ld2(tk + 4 * kz + 2, r);
+                const float4 xb = xb_rows[kz];
+                tmem_wait2(r);
+                const f2 dv = u2f2(r[0], r[1]);
+                y2[0] = fma2(dv, bc2(xb.x), y2[0]);
+                y2[1] = fma2(dv, bc2(xb.y), y2[1]);
+                y2[2] = fma2(dv, bc2(xb.z), y2[2]);
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------
 // RKHS contraction for the trajectory of this thread's team:
 //   y1[a] = sum_k K [t][k] * x1[k][a]      (trajectory.py:65 / :295)   t = 2*tl, 2*tl+1 packed
@@ -223,20 +376,21 @@ __device__ __forceinline__ void sincos_cw2(f2 x, f2 &S, f2 &C)
 // shared memory (KS) or, for T > 64, from L2/L1 through the read-only path.
 // SAME = true: x1 == x2 (forward evaluation), one operand load per k.
 // ---------------------------------------------------------------------------
-template <int WPT, bool KS, bool SAME>
+template <int WPT, int KS, bool SAME>
 __device__ __forceinline__ void contract(const float *__restrict__ kd, int T,
                                          const float4 *__restrict__ x1, const float4 *__restrict__ x2,
                                          f2 (&y1)[3], f2 (&y2)[3])
 {
     constexpr int STRIDE = 2 * WPT * 32 * R;       // floats per column k
-    constexpr int UNROLL = KS ? 5 : 8;
+    static_assert(KS == K_L2 || KS == K_SMEM, "the TMEM form is contract_tm");
+    constexpr int UNROLL = KS == K_SMEM ? 5 : 8;
 #pragma unroll
     for (int a = 0; a < 3; ++a) { y1[a] = bc2(0.0f); y2[a] = bc2(0.0f); }
 
 #pragma unroll UNROLL
     for (int k = 0; k < T; ++k) {
         float4 kv;
-        if constexpr (KS) kv = *reinterpret_cast<const float4 *>(kd + (size_t)k * STRIDE);
+        if constexpr (KS == K_SMEM) kv = *reinterpret_cast<const float4 *>(kd + (size_t)k * STRIDE);
         else kv = __ldg(reinterpret_cast<const float4 *>(kd + (size_t)k * STRIDE));
         const float4 xa = x1[k];
         float4 xb = xa;
@@ -259,19 +413,20 @@ __device__ __forceinline__ void contract(const float *__restrict__ kd, int T,
 // Skipped terms are exact zeros, so the result equals the dense sum bit for bit;
 // the visited terms are still accumulated in ascending k.
 // ---------------------------------------------------------------------------
-template <int WPT, bool KS>
+template <int WPT, int KS>
 __device__ __forceinline__ void contract_back(const float *__restrict__ ko, const float *__restrict__ kd, int T,
                                               const float4 *__restrict__ xa_rows, const float4 *__restrict__ xb_rows,
                                               const unsigned (&nz)[WPT][R], f2 (&y1)[3], f2 (&y2)[3])
 {
+    static_assert(KS == K_L2 || KS == K_SMEM, "the TMEM form is contract_back_tm");
     constexpr int SO = WPT * 32 * R, SD = 2 * WPT * 32 * R;
-    constexpr int UNROLL = KS ? 5 : 8;
+    constexpr int UNROLL = KS == K_SMEM ? 5 : 8;
 #pragma unroll
     for (int a = 0; a < 3; ++a) { y1[a] = bc2(0.0f); y2[a] = bc2(0.0f); }
 #pragma unroll UNROLL
     for (int k = 0; k < T; ++k) {
         float2 v;
-        if constexpr (KS) v = *reinterpret_cast<const float2 *>(ko + (size_t)k * SO);
+        if constexpr (KS == K_SMEM) v = *reinterpret_cast<const float2 *>(ko + (size_t)k * SO);
         else v = __ldg(reinterpret_cast<const float2 *>(ko + (size_t)k * SO));
         const float4 xa = xa_rows[k];
         const f2 kk = mk2(v.x, v.y);
@@ -291,7 +446,7 @@ __device__ __forceinline__ void contract_back(const float *__restrict__ ko, cons
                     const int k = (w * 32 + l) * R + r;
                     const float4 xb = xb_rows[k];
                     const float2 *col = reinterpret_cast<const float2 *>(kd + (size_t)k * SD + R);
-                    const f2 dv = KS ? col[0] : __ldg(col);
+                    const f2 dv = KS == K_SMEM ? col[0] : __ldg(col);
                     y2[0] = fma2(dv, bc2(xb.x), y2[0]);
                     y2[1] = fma2(dv, bc2(xb.y), y2[1]);
                     y2[2] = fma2(dv, bc2(xb.z), y2[2]);
@@ -373,13 +528,12 @@ __device__ __forceinline__ void obstacle_block(const float2 *__restrict__ obs, c
 // 0.8 and -0.8 of environment.py:43,57 (times 2 and 4) are applied once per sample.
 // ---------------------------------------------------------------------------
 template <int WPT, bool STRICT, bool ARM>
-__device__ __forceinline__ void cost_phase(const DevParams &p, const float2 *__restrict__ sObs, const Team<WPT> &G,
+__device__ __forceinline__ void cost_phase(const DevParams &p, const int T, const float2 *__restrict__ sObs, const Team<WPT> &G,
                                            const f2 (&yq)[3], const f2 (&yv)[3],
                                            const float *start, const float *goal, float lam_sg, float lam_jl,
                                            Rows<ARM> &Rw, float &loss, float &toc, int &ful)
 {
     constexpr int NJ = ARM ? 3 : 1;                        // joint positions charged with the obstacle potential
-    const int T = p.T;
     const int t0 = G.tl * R;
     const int lT = (T - 1) / R, rT = (T - 1) % R;          // team thread / row slot owning sample T-1
     const bool valid0 = t0 < T, valid1 = (t0 + 1) < T;
@@ -509,11 +663,10 @@ __device__ __forceinline__ void cost_phase(const DevParams &p, const float2 *__r
 // barrier that precedes the backward contraction (load_nz).
 // ---------------------------------------------------------------------------
 template <int WPT, bool ARM>
-__device__ __forceinline__ void grad_phase(const DevParams &p, const Team<WPT> &G, const Rows<ARM> &Rw, const float *start, const float *goal,
+__device__ __forceinline__ void grad_phase(const DevParams &p, const int T, const Team<WPT> &G, const Rows<ARM> &Rw, const float *start, const float *goal,
                                            float lam_sg, float lam_jl, float4 *XA, float4 *XB, unsigned (&nz)[WPT][R])
 {
     constexpr int NJ = ARM ? 3 : 1;
-    const int T = p.T;
     const int ta = G.tl * R, tb = ta + 1;
     const float w_hi = p.lam_max + p.w_avg;
     const f2 wt = mk2((ta == Rw.amax) ? w_hi : p.w_avg, (tb == Rw.amax) ? w_hi : p.w_avg);

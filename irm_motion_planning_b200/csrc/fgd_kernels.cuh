@@ -35,10 +35,10 @@ struct SmemLayout {
     __host__ __device__ size_t bytes() const { return (size_t)3 * k_floats * 4 + (size_t)obs_pairs * 8 + (size_t)n_teams * team_bytes(); }
 };
 
-__host__ __device__ inline SmemLayout make_layout(int T, int TP, int n_obs, bool ks, int n_teams, int wpt)
+__host__ __device__ inline SmemLayout make_layout(int T, int TP, int n_obs, int ksrc, int n_teams, int wpt)
 {
     SmemLayout l;
-    l.k_floats = ks ? T * TP : 0;
+    l.k_floats = ksrc == K_SMEM ? T * TP : 0;
     l.obs_pairs = (n_obs + 2) & ~1;
     l.x_rows = T | 1;     // odd row count: the operand buffers of neighbouring teams start 4 banks apart (mod 8)
     l.n_teams = n_teams;
@@ -50,11 +50,11 @@ __device__ __forceinline__ void hash_step(Slot &st, unsigned code) { st.hash = s
 
 // rows of this thread (alpha, a candidate, ...) into an operand buffer
 template <int WPT>
-__device__ __forceinline__ void write_rows(const DevParams &p, const Team<WPT> &G, const f2 (&c)[3], float4 *X)
+__device__ __forceinline__ void write_rows(const int T, const Team<WPT> &G, const f2 (&c)[3], float4 *X)
 {
     const int t = G.tl * R;
-    if (t < p.T) X[t] = make_float4(c[0].x, c[1].x, c[2].x, 0.0f);
-    if (t + 1 < p.T) X[t + 1] = make_float4(c[0].y, c[1].y, c[2].y, 0.0f);
+    if (t < T) X[t] = make_float4(c[0].x, c[1].x, c[2].x, 0.0f);
+    if (t + 1 < T) X[t + 1] = make_float4(c[0].y, c[1].y, c[2].y, 0.0f);
 }
 
 // candidate  (1 - lam_reg*lr) * alpha - lr * dir      optimizer_BLS.py:139, optimizer_GD.py:185
@@ -151,11 +151,11 @@ __device__ __forceinline__ void fetch_slot(const DevParams &p, const Team<WPT> &
 // barrier's phase 0.  The obstacle set (8 B granules, any count) is staged by the threads meanwhile.
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
-template <bool KS>
+template <int KS>
 __device__ __forceinline__ void stage_constants(const DevParams &p, const SmemLayout &L, float *sKD, float *sKO, float2 *sObs, int nthreads)
 {
     __shared__ __align__(8) unsigned long long tma_bar;
-    if constexpr (KS) {
+    if constexpr (KS == K_SMEM) {
         const unsigned bar = smem_u32(&tma_bar);
         if (threadIdx.x == 0) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
@@ -177,7 +177,7 @@ __device__ __forceinline__ void stage_constants(const DevParams &p, const SmemLa
         const int i = i0 + threadIdx.x;
         if (i < L.obs_pairs) sObs[i] = (i < p.n_obs) ? make_float2(p.obs[2 * i], p.obs[2 * i + 1]) : make_float2(0.f, 0.f);
     }
-    if constexpr (KS) {
+    if constexpr (KS == K_SMEM) {
         const unsigned bar = smem_u32(&tma_bar);
         unsigned done = 0;
         while (!done) {
@@ -188,6 +188,46 @@ __device__ __forceinline__ void stage_constants(const DevParams &p, const SmemLa
     __syncthreads();
 }
 
+// K / dK operand table -> tensor memory (see fgd_device.cuh): warp 0 allocates TMEM_COLS columns, warps 0..3 write
+// the table into their lane quadrant (lane l, columns 4k..4k+3 = KD[k][l]), every warp gets the address of the
+// quadrant it may read.  CTA-uniform control flow; call once, before the main loop.
+__device__ __forceinline__ unsigned tmem_stage_tables(const DevParams &p)
+{
+    __shared__ unsigned tm_base;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tm_base)), "r"((unsigned)TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tk = tm_base + ((unsigned)((warp & 3) * 32) << 16);
+    if (warp < 4) {
+        const float4 *src = reinterpret_cast<const float4 *>(p.KD) + lane;      // KD[k][lane][4], 32 lanes per k
+#pragma unroll 1
+        for (int k = 0; k < p.T; ++k) {
+            const float4 v = __ldg(src + (size_t)k * 32);
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tk + 4 * k), "r"(__float_as_uint(v.x)),
+                         "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)), "r"(__float_as_uint(v.w)) : "memory");
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    return tk;
+}
+
+// every warp of the CTA is done with the tables: give the columns back
+__device__ __forceinline__ void tmem_release_tables(unsigned tk)
+{
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if ((threadIdx.x >> 5) == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tk & 0x0000ffffu), "r"((unsigned)TMEM_COLS) : "memory");
+}
+
 // ---------------------------------------------------------------------------
 // Persistent optimiser: every team of WPT warps runs one trajectory as an
 // autonomous state machine and keeps pulling trajectories until the batch queue
@@ -195,13 +235,16 @@ __device__ __forceinline__ void stage_constants(const DevParams &p, const SmemLa
 // (candidate evaluation or gradient).  NW warps per CTA; WPT > 1 requires
 // NW == WPT (the CTA barrier is the team barrier).
 // ---------------------------------------------------------------------------
-template <int WPT, bool STRICT, bool KS, int NW, int MINB, bool ARM>
+// TC > 0: instance specialised for T == TC (the reference's default T = 50): the contraction loops are fully unrolled.
+template <int WPT, bool STRICT, int KS, int NW, int MINB, bool ARM, int TC>
 __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __grid_constant__ DevParams p)
 {
+    static_assert(TC == 0 || KS == K_TMEM, "compile-time T: TMEM instances only");
     static_assert(WPT == 1 || NW == WPT, "multi-warp teams own their CTA");
+    static_assert(KS != K_TMEM || (WPT == 1 && NW >= 4 && NW % 4 == 0), "TMEM tables: single-warp teams, whole lane quadrants");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int TEAMS = NW / WPT;
-    const int T = p.T;
+    const int T = TC > 0 ? TC : p.T;
     const SmemLayout L = make_layout(T, WPT * 32 * R, p.n_obs, KS, TEAMS, WPT);
     float *sKD = reinterpret_cast<float *>(smem_raw);
     float *sKO = sKD + 2 * L.k_floats;
@@ -212,8 +255,11 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
     const int team = (threadIdx.x >> 5) / WPT;
     float4 *XA = reinterpret_cast<float4 *>(sTeams + (size_t)team * L.team_bytes()), *XB = XA + L.x_rows;
     const Team<WPT> G(reinterpret_cast<float *>(XB + L.x_rows));
-    const float *kd = (KS ? sKD : p.KD) + G.tl * 2 * R;
-    const float *ko = (KS ? sKO : p.KO) + G.tl * R;
+    const float *kd = (KS == K_SMEM ? sKD : p.KD) + G.tl * 2 * R;
+    const float *ko = (KS == K_SMEM ? sKO : p.KO) + G.tl * R;
+    unsigned tk = 0;
+    if constexpr (KS == K_TMEM) tk = tmem_stage_tables(p);
+    (void)kd; (void)ko; (void)tk;
 
     int kind = K_IDLE;
     Slot st;                   // team-uniform loop state of this team's trajectory (registers)
@@ -235,8 +281,13 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
         if (!boot) {
             if (kind == K_IDLE) break;
             G.sync();                                                                    // operands complete
-            if (kind != K_BACK) contract<WPT, KS, true>(kd, T, XA, XA, y1, y2);          // forward: K x, dK x
-            else { load_nz<WPT>(G, nz); contract_back<WPT, KS>(ko, kd, T, XA, XB, nz, y1, y2); }   // backward: K G_q + dK (-G_v)
+            if constexpr (KS == K_TMEM) {
+                if (kind != K_BACK) contract_tm<true, TC>(tk, T, XA, XA, y1, y2);                // forward: K x, dK x
+                else contract_back_tm<TC>(tk, T, XA, XB, nz, y1, y2);                            // backward: K G_q + dK (-G_v)
+            } else {
+                if (kind != K_BACK) contract<WPT, KS, true>(kd, T, XA, XA, y1, y2);
+                else { load_nz<WPT>(G, nz); contract_back<WPT, KS>(ko, kd, T, XA, XB, nz, y1, y2); }
+            }
             G.sync();                                                                    // operands consumed
         }
         PCLK(was_back ? 4 : 0);
@@ -276,7 +327,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
             Rows<ARM> Rw;
             float loss_c, toc_c;
             int ful_c;
-            cost_phase<WPT, STRICT, ARM>(p, sObs, G, y1, y2, st.start, st.goal, st.lam_sg, st.lam_jl, Rw, loss_c, toc_c, ful_c);
+            cost_phase<WPT, STRICT, ARM>(p, T, sObs, G, y1, y2, st.start, st.goal, st.lam_sg, st.lam_jl, Rw, loss_c, toc_c, ful_c);
             PCLK(1);
             bool accept = false;
             if (kind == K_EVAL0) {
@@ -319,7 +370,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
                     else { st.inner += 1; want_head = true; }
                 }
             }
-            if (accept) grad_phase<WPT, ARM>(p, G, Rw, st.start, st.goal, st.lam_sg, st.lam_jl, XA, XB, nz);
+            if (accept) grad_phase<WPT, ARM>(p, T, G, Rw, st.start, st.goal, st.lam_sg, st.lam_jl, XA, XB, nz);
         }
         PCLK(was_back ? 5 : 2);
         // ---- common tail: loop heads, retirement, refill -------------------------------------
@@ -355,13 +406,13 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
         if (want_eval) {
             // (re)start with the loss and gradient operands at the current alpha: optimizer_BLS.py:163, optimizer_GD.py:210
             if (p.mode == 1) st.lr = p.gd_lr[st.outer];
-            write_rows<WPT>(p, G, a, XA);
+            write_rows<WPT>(T, G, a, XA);
             kind = K_EVAL0;
         }
         if (want_cand) {
             f2 c[3];
             make_candidate(p, st.lr, a, d, c);
-            write_rows<WPT>(p, G, c, XA);
+            write_rows<WPT>(T, G, c, XA);
         }
         boot = false;
         PCLK(was_back ? 6 : 3);
@@ -373,13 +424,14 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
     if (p.dbg && blockIdx.x == 0 && G.tl == 0 && pc[7] > 2)
         for (int i = 0; i < 8; ++i) p.dbg[i] = (int)(pc[i] >> 4);      // units of 16 cycles
 #endif
+    if constexpr (KS == K_TMEM) tmem_release_tables(tk);
 }
 
 // ---------------------------------------------------------------------------
 // Evaluation only (unit-parity hook and the host's compute_trajectory_cost*):
 // one team per trajectory, grid-stride.
 // ---------------------------------------------------------------------------
-template <int WPT, bool STRICT, bool KS, int NW, bool ARM>
+template <int WPT, bool STRICT, int KS, int NW, bool ARM>
 __global__ void __launch_bounds__(NW * 32) fgd_eval_kernel(const __grid_constant__ DevParams p, const EvalPtrs e)
 {
     static_assert(WPT == 1 || NW == WPT, "multi-warp teams own their CTA");
@@ -396,7 +448,7 @@ __global__ void __launch_bounds__(NW * 32) fgd_eval_kernel(const __grid_constant
     const int team = (threadIdx.x >> 5) / WPT;
     float4 *XA = reinterpret_cast<float4 *>(sTeams + (size_t)team * L.team_bytes()), *XB = XA + L.x_rows;
     const Team<WPT> G(reinterpret_cast<float *>(XB + L.x_rows));
-    const float *kd = (KS ? sKD : p.KD) + G.tl * 2 * R;
+    const float *kd = (KS == K_SMEM ? sKD : p.KD) + G.tl * 2 * R;
     const int stride = gridDim.x * TEAMS;
     const int t0 = G.tl * R;
 
@@ -415,7 +467,7 @@ __global__ void __launch_bounds__(NW * 32) fgd_eval_kernel(const __grid_constant
         Rows<ARM> Rw;
         float loss, toc;
         int ful;
-        cost_phase<WPT, STRICT, ARM>(p, sObs, G, y1, y2, start, goal, e.lam_sg, e.lam_jl, Rw, loss, toc, ful);
+        cost_phase<WPT, STRICT, ARM>(p, T, sObs, G, y1, y2, start, goal, e.lam_sg, e.lam_jl, Rw, loss, toc, ful);
         if (G.tl == 0) {
             if (e.loss) e.loss[b] = loss;
             if (e.toc) e.toc[b] = toc;
@@ -434,7 +486,7 @@ __global__ void __launch_bounds__(NW * 32) fgd_eval_kernel(const __grid_constant
         }
         if (e.grad) {
             unsigned nz_unused[WPT][R];
-            grad_phase<WPT, ARM>(p, G, Rw, start, goal, e.lam_sg, e.lam_jl, XA, XB, nz_unused);
+            grad_phase<WPT, ARM>(p, T, G, Rw, start, goal, e.lam_sg, e.lam_jl, XA, XB, nz_unused);
             G.sync();
             contract<WPT, KS, false>(kd, T, XA, XB, y1, y2);      // dense reference form of the backward contraction
             f2 g[3];

@@ -1,0 +1,106 @@
+// Throughput probe: per-lane table reads from TMEM (tcgen05.ld 32x32b) vs shared memory (LDS.128), alone and mixed.
+// Question: is TMEM read bandwidth additive to the shared-memory data pipe, and how many bytes/cycle/SM does it give?
+#include <cstdio>
+#include <cuda_runtime.h>
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+template <int MODE>
+__global__ void __launch_bounds__(256, 2) k(int iters, float *sink, long long *cyc)
+{
+    __shared__ unsigned tbase;
+    __shared__ __align__(16) float tab[64 * 32 * 4];      // [k][lane][4]: 32 KB
+    for (int i = threadIdx.x; i < 64 * 32 * 4; i += 256) tab[i] = (float)(i & 255) * 1e-3f;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(&tbase)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tb = tbase + ((unsigned)((warp & 3) * 32) << 16);
+    if (warp < 4) {
+        for (int c = 0; c < 256; c += 4) {
+            const float v = (float)(c + lane) * 1e-3f;
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tb + c), "r"(__float_as_uint(v)),
+                         "r"(__float_as_uint(v + 1.f)), "r"(__float_as_uint(v + 2.f)), "r"(__float_as_uint(v + 3.f)) : "memory");
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    float2 a0 = make_float2(0, 0), a1 = a0, a2 = a0, a3 = a0;
+    const float4 *mine = reinterpret_cast<const float4 *>(tab) + lane;
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int g = 0; g < 64; g += 4) {
+            unsigned r[16];
+            float4 s[4];
+            if (MODE == 0 || MODE == 3 || MODE == 4) {          // 4 x (x4) TMEM loads = 4 k's
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(r[4 * u]), "=r"(r[4 * u + 1]), "=r"(r[4 * u + 2]), "=r"(r[4 * u + 3]) : "r"(tb + 4 * (g + u)));
+            }
+            if (MODE == 1) {                                      // one x16 TMEM load = 4 k's
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                             : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                               "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(tb + 4 * g));
+            }
+            if (MODE == 2 || MODE == 3) {                         // 4 per-lane LDS.128 (4 wavefronts each)
+#pragma unroll
+                for (int u = 0; u < 4; ++u) s[u] = mine[(g + u) * 32];
+            }
+            if (MODE == 4) {                                      // 4 broadcast LDS.128 (1 wavefront each) as in the contraction
+#pragma unroll
+                for (int u = 0; u < 4; ++u) s[u] = reinterpret_cast<const float4 *>(tab)[(g + u + it) & 63];
+            }
+            if (MODE != 2) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (MODE != 2) {
+                    a0 = __ffma2_rn(make_float2(__uint_as_float(r[4 * u]), __uint_as_float(r[4 * u + 1])), make_float2(1.0001f, 1.0001f), a0);
+                    a1 = __ffma2_rn(make_float2(__uint_as_float(r[4 * u + 2]), __uint_as_float(r[4 * u + 3])), make_float2(1.0001f, 1.0001f), a1);
+                }
+                if (MODE == 2 || MODE == 3 || MODE == 4) {
+                    a2 = __ffma2_rn(make_float2(s[u].x, s[u].y), make_float2(1.0001f, 1.0001f), a2);
+                    a3 = __ffma2_rn(make_float2(s[u].z, s[u].w), make_float2(1.0001f, 1.0001f), a3);
+                }
+            }
+        }
+    }
+    const long long t1 = clock64();
+    const float r = a0.x + a0.y + a1.x + a1.y + a2.x + a2.y + a3.x + a3.y;
+    if (r == 123456.789f) sink[0] = r;
+    if (threadIdx.x == 0 && blockIdx.x == 0) cyc[0] = t1 - t0;
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tbase) : "memory");
+}
+template <int MODE> void run(const char *name, double bytes_per_k)
+{
+    float *sink; long long *cyc; cudaMalloc(&sink, 4); cudaMalloc(&cyc, 8);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int grid = 148 * 2, iters = 2000;
+    double best = 1e30; long long c = 0;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(e0); k<MODE><<<grid, 256>>>(iters, sink, cyc); cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        if (rep && ms < best) { best = ms; cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost); }
+    }
+    cudaError_t e = cudaGetLastError();
+    // per SM: 16 warps x iters x 64 k's; cycles from clock64 of one warp (all warps run concurrently)
+    const double k_per_sm = 16.0 * iters * 64;
+    printf("%-44s %8.3f ms  %9lld cyc  %.2f cyc per warp-k per SM  (%.0f B/cyc/SM)  %s\n", name, best, c, c / k_per_sm,
+           bytes_per_k * k_per_sm / c, cudaGetErrorString(e));
+}
+int main()
+{
+    run<0>("TMEM 32x32b.x4 per k (512 B/warp)", 512);
+    run<1>("TMEM 32x32b.x16 per 4 k", 512);
+    run<2>("LDS.128 per lane per k (4 wavefronts)", 512);
+    run<3>("TMEM x4 + LDS.128 per lane, per k", 1024);
+    run<4>("TMEM x4 + broadcast LDS.128, per k", 512 + 16);
+    return 0;
+}

@@ -48,28 +48,27 @@ inline int warps_per_trajectory(int T) { return T <= 64 ? 1 : (T <= 128 ? 2 : 4)
 // (variant, WPT, KSRC, NW, MINB): the instantiated optimiser kernels.  WPT warps per trajectory; KSRC: where the K tables
 // live - tensor memory (K_TMEM, T <= 64), shared memory (K_SMEM, T <= 64) or L2 (K_L2); NW warps per CTA (= WPT for
 // multi-warp teams), MINB = min CTAs per SM (register cap).  Variant 0 is the default; variant 1 exists for A/B
-// measurements (env FGD_VARIANT): the shared-memory tables for T <= 64, other register caps for the team kernels.
+// measurements (env FGD_VARIANT): the shared-memory tables for T <= 64.
 #define FGD_FOR_CONFIGS(X) \
     X(0, 1, K_TMEM, 16, 1) X(0, 2, K_L2, 2, 8) X(0, 4, K_L2, 4, 4) \
-    X(1, 1, K_SMEM, 8, 2) X(1, 2, K_L2, 2, 6) X(1, 4, K_L2, 4, 3) \
-    X(2, 1, K_TMEM, 8, 2)
+    X(1, 1, K_SMEM, 8, 2)
 // (WPT, KSRC, NW): the evaluation kernels (parity hook; tables in shared memory / L2)
 #define FGD_FOR_EVAL_CONFIGS(X) X(1, K_SMEM, 8) X(2, K_L2, 2) X(4, K_L2, 4)
 
-template <int WPT, bool STRICT, int KS, int NW, int MINB, bool ARM, int TC = 0>
+template <int WPT, bool STRICT, int KS, int NW, int MINB, bool ARM, int TC>
 cudaError_t launch_opt(const DevParams &p, int grid, size_t smem, cudaStream_t st)
 {
-    auto kern = fgd_optimize_kernel<WPT, STRICT, KS, NW, MINB, ARM, TC>;
+    auto kern = p.mode == 0 ? fgd_optimize_kernel<WPT, STRICT, KS, NW, MINB, ARM, TC, 0> : fgd_optimize_kernel<WPT, STRICT, KS, NW, MINB, ARM, TC, 1>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, NW * 32, smem, st>>>(p);
     return cudaGetLastError();
 }
 
-template <int WPT, bool STRICT, int KS, int NW, int MINB, bool ARM, int TC = 0>
+template <int WPT, bool STRICT, int KS, int NW, int MINB, bool ARM, int TC>
 int occupancy_opt(size_t smem)
 {
-    auto kern = fgd_optimize_kernel<WPT, STRICT, KS, NW, MINB, ARM, TC>;
+    auto kern = fgd_optimize_kernel<WPT, STRICT, KS, NW, MINB, ARM, TC, 0>;      // both modes share the launch bounds
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int nb = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, NW * 32, smem) != cudaSuccess) nb = 1;
@@ -130,27 +129,38 @@ int warps_per_cta(int v, int WPT)
     return WPT;
 }
 
-// The default single-warp kernel has an instance specialised for the reference's default T (main.py: --n-timesteps 50).
+// The tensor-memory kernels have an instance specialised for the reference's default T (main.py: --n-timesteps 50).
 constexpr int FGD_TC = 50;
-inline bool use_tc(int v, int WPT, int T)
+inline bool use_tc(int T)
 {
     static const bool off = [] { const char *e = std::getenv("FGD_NO_TC"); return e && e[0] == '1'; }();
-    return !off && v == 0 && WPT == 1 && T == FGD_TC;
+    return !off && T == FGD_TC;
+}
+
+// the whole-arm cost variants exist for runtime T only (TC = 0)
+template <int W, int KS, int NW, int MB, int TC>
+cudaError_t launch_sa(bool strict, bool arm, const DevParams &p, int grid, size_t smem, cudaStream_t st)
+{
+    return arm ? (strict ? launch_opt<W, true, KS, NW, MB, true, 0>(p, grid, smem, st) : launch_opt<W, false, KS, NW, MB, true, 0>(p, grid, smem, st))
+               : (strict ? launch_opt<W, true, KS, NW, MB, false, TC>(p, grid, smem, st) : launch_opt<W, false, KS, NW, MB, false, TC>(p, grid, smem, st));
+}
+
+template <int W, int KS, int NW, int MB, int TC>
+int occupancy_sa(bool strict, bool arm, size_t smem)
+{
+    return arm ? (strict ? occupancy_opt<W, true, KS, NW, MB, true, 0>(smem) : occupancy_opt<W, false, KS, NW, MB, true, 0>(smem))
+               : (strict ? occupancy_opt<W, true, KS, NW, MB, false, TC>(smem) : occupancy_opt<W, false, KS, NW, MB, false, TC>(smem));
 }
 
 cudaError_t dispatch_opt(int v, int WPT, bool strict, bool arm, const DevParams &p, int grid, size_t smem, cudaStream_t st)
 {
-    if (use_tc(v, WPT, p.T))
-        return arm ? (strict ? launch_opt<1, true, K_TMEM, 16, 1, true, FGD_TC>(p, grid, smem, st)
-                             : launch_opt<1, false, K_TMEM, 16, 1, true, FGD_TC>(p, grid, smem, st))
-                   : (strict ? launch_opt<1, true, K_TMEM, 16, 1, false, FGD_TC>(p, grid, smem, st)
-                             : launch_opt<1, false, K_TMEM, 16, 1, false, FGD_TC>(p, grid, smem, st));
-#define X(V_, W_, KS_, NW_, MB_)                                                        \
-    if (v == V_ && WPT == W_)                                                            \
-        return arm ? (strict ? launch_opt<W_, true, KS_, NW_, MB_, true>(p, grid, smem, st)      \
-                             : launch_opt<W_, false, KS_, NW_, MB_, true>(p, grid, smem, st))    \
-                   : (strict ? launch_opt<W_, true, KS_, NW_, MB_, false>(p, grid, smem, st)     \
-                             : launch_opt<W_, false, KS_, NW_, MB_, false>(p, grid, smem, st));
+#define X(V_, W_, KS_, NW_, MB_)                                                                             \
+    if (v == V_ && WPT == W_) {                                                                               \
+        if constexpr (KS_ == K_TMEM) {                                                                        \
+            if (use_tc(p.T)) return launch_sa<W_, KS_, NW_, MB_, FGD_TC>(strict, arm, p, grid, smem, st);     \
+        }                                                                                                     \
+        return launch_sa<W_, KS_, NW_, MB_, 0>(strict, arm, p, grid, smem, st);                               \
+    }
     FGD_FOR_CONFIGS(X)
 #undef X
     return cudaErrorInvalidValue;
@@ -158,13 +168,13 @@ cudaError_t dispatch_opt(int v, int WPT, bool strict, bool arm, const DevParams 
 
 int dispatch_occ(int v, int WPT, int T, bool strict, bool arm, size_t smem)
 {
-    if (use_tc(v, WPT, T))
-        return arm ? (strict ? occupancy_opt<1, true, K_TMEM, 16, 1, true, FGD_TC>(smem) : occupancy_opt<1, false, K_TMEM, 16, 1, true, FGD_TC>(smem))
-                   : (strict ? occupancy_opt<1, true, K_TMEM, 16, 1, false, FGD_TC>(smem) : occupancy_opt<1, false, K_TMEM, 16, 1, false, FGD_TC>(smem));
-#define X(V_, W_, KS_, NW_, MB_)                                                        \
-    if (v == V_ && WPT == W_)                                                            \
-        return arm ? (strict ? occupancy_opt<W_, true, KS_, NW_, MB_, true>(smem) : occupancy_opt<W_, false, KS_, NW_, MB_, true>(smem))   \
-                   : (strict ? occupancy_opt<W_, true, KS_, NW_, MB_, false>(smem) : occupancy_opt<W_, false, KS_, NW_, MB_, false>(smem));
+#define X(V_, W_, KS_, NW_, MB_)                                                                             \
+    if (v == V_ && WPT == W_) {                                                                               \
+        if constexpr (KS_ == K_TMEM) {                                                                        \
+            if (use_tc(T)) return occupancy_sa<W_, KS_, NW_, MB_, FGD_TC>(strict, arm, smem);                 \
+        }                                                                                                     \
+        return occupancy_sa<W_, KS_, NW_, MB_, 0>(strict, arm, smem);                                         \
+    }
     FGD_FOR_CONFIGS(X)
 #undef X
     return 1;

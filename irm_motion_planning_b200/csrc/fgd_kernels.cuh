@@ -96,7 +96,7 @@ __device__ __forceinline__ void save_slot(const DevParams &p, const Team<WPT> &G
 }
 
 // Pull the next unfinished trajectory from the batch queue (team-uniform).
-template <int WPT>
+template <int WPT, int MODE>
 __device__ __forceinline__ void fetch_slot(const DevParams &p, const Team<WPT> &G, Slot &st, int &kind, f2 (&a)[3], float *stage)
 {
     for (;;) {
@@ -120,7 +120,7 @@ __device__ __forceinline__ void fetch_slot(const DevParams &p, const Team<WPT> &
         st.done_iters = 0; st.j = 0; st.alpha_norm = 0.0f;
         if (status == FGD_ST_FRESH) {
             st.lam_sg = p.lam_sg0; st.lam_jl = p.lam_jl0;
-            st.lr = (p.mode == 0) ? p.bls_lr0 : p.gd_lr[0];
+            st.lr = (MODE == 0) ? p.bls_lr0 : p.gd_lr[0];
             st.outer = 0; st.inner = 0; st.inner_total = 0; st.cand_evals = 0; st.accepts = 0; st.ful = 0; st.hash = 0u;
             st.loss = 0.0f; st.toc = 0.0f; st.last_new = 0.0f;
         } else {
@@ -236,7 +236,9 @@ __device__ __forceinline__ void tmem_release_tables(unsigned tk)
 // NW == WPT (the CTA barrier is the team barrier).
 // ---------------------------------------------------------------------------
 // TC > 0: instance specialised for T == TC (the reference's default T = 50): the contraction loops are fully unrolled.
-template <int WPT, bool STRICT, int KS, int NW, int MINB, bool ARM, int TC>
+// MODE: 0 = backtracking line search (optimizer_BLS.py), 1 = gradient descent (optimizer_GD.py) - a compile-time
+// constant so that each instance carries only its own state machine.
+template <int WPT, bool STRICT, int KS, int NW, int MINB, bool ARM, int TC, int MODE>
 __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __grid_constant__ DevParams p)
 {
     static_assert(TC == 0 || KS == K_TMEM, "compile-time T: TMEM instances only");
@@ -302,13 +304,13 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
             f2 g[3];
             backward_rows(p, y1, y2, g);
             float alpha_norm = 0.0f;
-            if (p.mode == 0) {
+            if (MODE == 0) {
                 const bool v0 = G.tl * R < T, v1 = G.tl * R + 1 < T;
                 float part = 0.0f;
                 const f2 ss = ss3_2(g[0], g[1], g[2]);
                 if (v0) part = part + ss.x;
                 if (v1) part = part + ss.y;
-                const float scale = 1.0f / sqrtf(tsum<WPT>(G, part, XCH_NORM));          // optimizer_BLS.py:165
+                const float scale = 1.0f / sqrtf(tsum<WPT>(G, part, XCH_NORM));          // optimizer_BLS.py:165 (MUFU.RSQ measured: < 1 % gain, not taken)
                 float pb = 0.0f;
                 const f2 n0 = mul2(g[0], bc2(scale)), n1 = mul2(g[1], bc2(scale)), n2 = mul2(g[2], bc2(scale));
                 const f2 pp = mul2(add2(add2(g[0], g[1]), g[2]), add2(add2(n0, n1), n2));
@@ -338,7 +340,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
                 const float lr = st.lr, loss = st.loss;
                 const bool minimized = (loss - loss_c < p.eps_loop);               // optimizer_BLS.py:178, optimizer_GD.py:194
                 bool rejected = false;
-                if (p.mode == 0) {                                                 // Armijo test, optimizer_BLS.py:141-149
+                if (MODE == 0) {                                                   // Armijo test, optimizer_BLS.py:141-149
                     const float req = loss - (p.bls_alpha * lr) * st.alpha_norm;
                     rejected = loss_c > req;
                 } else {
@@ -355,7 +357,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
                         if (loss - loss < p.eps_loop) { hash_step(st, 3u); want_end = true; }
                         else { st.inner += 1; want_eval = true; }
                     }
-                } else if (p.mode == 1 && minimized) {
+                } else if (MODE == 1 && minimized) {
                     hash_step(st, 3u); want_end = true;    // GD: the candidate is discarded (optimizer_GD.py:191-192)
                 } else {
                     f2 c[3];
@@ -363,7 +365,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
 #pragma unroll
                     for (int b = 0; b < 3; ++b) a[b] = c[b];
                     accept = true;
-                    if (p.mode == 0) st.lr = lr * p.bls_bp;
+                    if (MODE == 0) st.lr = lr * p.bls_bp;
                     st.accepts += 1; hash_step(st, 2u);
                     st.ful = ful_c; st.toc = toc_c; st.last_new = loss_c; st.loss = loss_c;
                     if (minimized) { hash_step(st, 3u); want_end = true; }       // BLS keeps the accepted alpha
@@ -385,7 +387,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
         }
         bool retire = false;
         if (want_end) {                                          // optimizer_BLS.py:196-205, optimizer_GD.py:214-224
-            const bool dual = (p.mode == 0) || (p.max_outer > 1);
+            const bool dual = (MODE == 0) || (p.max_outer > 1);
             retire = !dual || st.ful;
             if (!retire) {
                 st.lam_sg = st.lam_sg * p.lam_inc; st.lam_jl = st.lam_jl * p.lam_inc;
@@ -394,18 +396,18 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
             }
             if (!retire) {
                 st.inner = 0;
-                if (p.mode == 0) st.lr = p.bls_lr0;              // optimizer_BLS.py:193
+                if (MODE == 0) st.lr = p.bls_lr0;              // optimizer_BLS.py:193
                 want_eval = true;
             }
         }
         if (retire || save_active || boot) {
             if (!boot) save_slot<WPT>(p, G, st, retire ? FGD_ST_DONE : FGD_ST_ACTIVE, a, reinterpret_cast<float *>(XA));
-            fetch_slot<WPT>(p, G, st, kind, a, reinterpret_cast<float *>(XA));
+            fetch_slot<WPT, MODE>(p, G, st, kind, a, reinterpret_cast<float *>(XA));
             want_eval = (kind != K_IDLE);
         }
         if (want_eval) {
             // (re)start with the loss and gradient operands at the current alpha: optimizer_BLS.py:163, optimizer_GD.py:210
-            if (p.mode == 1) st.lr = p.gd_lr[st.outer];
+            if (MODE == 1) st.lr = p.gd_lr[st.outer];
             write_rows<WPT>(T, G, a, XA);
             kind = K_EVAL0;
         }

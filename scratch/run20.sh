@@ -1,0 +1,17 @@
+#!/bin/bash
+mkdir -p gpurun_out
+OUT=gpurun_out/run20.txt
+: > $OUT
+summ() { python -c "
+import sys,json
+for l in sys.stdin:
+    l=l.strip()
+    if l.startswith('{'):
+        d=json.loads(l); e=d.get('e2e') or {}
+        print('$1', 'value=%.4g'%d['value'], 'ms=%.4g'%d['ms_per_step'], 'frac=%.3f'%d['roofline']['frac'], 'it=%.2f'%d['mean_inner_iters'], 'ful=%.3f'%d['fulfilled_frac'])
+"; }
+for lib in irm_motion_planning_b200/libfgd_b200.so scratch/libfgd_ieee_rsqrt.so; do
+FGD_LIBRARY=$PWD/$lib timeout 300 python bench.py --workload c5 --batch 262144 --steps 3 --warmup 1 --no-cpu-baseline --no-e2e 2>>gpurun_out/run20.err | summ "$lib c5 B262144" >> $OUT
+FGD_LIBRARY=$PWD/$lib timeout 300 python bench.py --workload c1 --steps 20 --warmup 3 --no-cpu-baseline --no-e2e 2>>gpurun_out/run20.err | summ "$lib c1" >> $OUT
+done
+cat $OUT; tail -5 gpurun_out/run20.err

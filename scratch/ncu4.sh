@@ -11,4 +11,4 @@ run() {
   rm -f gpurun_out/${TAG}.ncu-rep
   tail -2 gpurun_out/${TAG}_ncu.log
 }
-run ${V:-0} c2 65536 ${TAG:-r01g_c2_b65536_tmem}
+run ${V:-0} c2 ${B:-65536} ${TAG:-r01h_c2_b65536}

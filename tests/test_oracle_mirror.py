@@ -231,3 +231,26 @@ def test_whole_arm_cost_extension():
     # end to end on the default problem: converges, constraints fulfilled
     a, fs, is_ = m.optimize(tm32.init_trajectory(START, GOAL)[None], START, GOAL)
     assert is_[0, M.I_STATUS] == M.ST_DONE and is_[0, M.I_FULFILLED] == 1
+
+
+def test_fast_mode_division_by_T_equals_ieee_division():
+    """Fast-math CUDA replaces x / T (trajectory.py:88,228,255) by q0 = x * RN(1/T); q = fma(fma(-q0, T, x), RN(1/T), q0)
+    (csrc/fgd_device.cuh div_T).  With an exact remainder that is the correctly rounded quotient for finite x, i.e. the
+    same bits as the oracle's IEEE division: checked here with exact rational arithmetic standing in for the FMAs."""
+    from fractions import Fraction
+
+    def rn(fr):                       # round a rational to the nearest float32, ties to even
+        f = np.float32(float(fr))
+        cands = [f, np.nextafter(f, np.float32(np.inf)), np.nextafter(f, np.float32(-np.inf))]
+        return min(cands, key=lambda c: (abs(Fraction(float(c)) - fr), int(np.float32(c).view(np.uint32)) & 1))
+
+    rng = np.random.default_rng(7)
+    for T in (50, 2, 3, 7, 33, 64, 100, 129, 255, 256):
+        y = np.float32(T)
+        r = np.float32(1.0) / y
+        xs = np.concatenate([rng.uniform(0, 200, 300), np.exp(rng.uniform(-20, 20, 300)), T * rng.integers(1, 1000, 60)]).astype(np.float32)
+        for x in xs:
+            q0 = np.float32(x * r)
+            rem = rn(Fraction(float(x)) - Fraction(float(q0)) * Fraction(float(y)))
+            q1 = rn(Fraction(float(rem)) * Fraction(float(r)) + Fraction(float(q0)))
+            assert q1 == np.float32(x / y), (T, x)

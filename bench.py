@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--strict-math", action="store_true")
     ap.add_argument("--whole-arm", action="store_true", help="obstacle cost over all joint positions (SURVEY 8f-3) instead of the end effector")
+    ap.add_argument("--presoak-seconds", type=float, default=1.0,
+                    help="untimed repetitions of the step before the W warm-up steps, so that the GPU has left its idle clocks")
     ap.add_argument("--no-saturated", action="store_true", help="skip the secondary large-batch measurement of the default run")
     ap.add_argument("--saturated-batch", type=int, default=65536)
     return ap.parse_args()
@@ -251,6 +253,23 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    # pre-soak (untimed): the host-side input generation above leaves the GPU idle for seconds; the first steps after that
+    # run at ramping clocks (measured on c5 at N = 2: 487 / 378 / 359 ms for three consecutive steps), so the step is
+    # repeated for --presoak-seconds before the W warm-up steps
+    # (the repetition count is agreed across ranks: a step may contain a collective)
+    if a.presoak_seconds > 0:
+        torch.cuda.synchronize()
+        t_one = time.perf_counter()
+        one_step(bufs[0])
+        torch.cuda.synchronize()
+        dt_one = torch.tensor([time.perf_counter() - t_one], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt_one, op=dist.ReduceOp.MAX)
+        for _ in range(int(min(5000, a.presoak_seconds / max(float(dt_one.item()), 1e-6)))):
+            bufs[0].copy_(a0_dev)
+            one_step(bufs[0])
+        torch.cuda.synchronize()
+    bufs[0].copy_(a0_dev)
     for i in range(a.warmup):
         if n_buf < n_total:
             bufs[i % n_buf].copy_(a0_dev)
@@ -277,6 +296,8 @@ def main():
     total_s = sum(step_ms) * 1e-3
     t_max = torch.tensor([total_s], dtype=torch.float64, device=dev)
     if world > 1:
+        print(f"[bench] rank {rank}: {1e3 * total_s / a.steps:.3f} ms per step on its own device "
+              f"(steps: {', '.join('%.2f' % m for m in step_ms)})", file=sys.stderr, flush=True)
         dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
     total_s = float(t_max.item())
 
@@ -389,7 +410,8 @@ def main():
                                   math="strict" if a.strict_math else "fast (rcp.approx)"),
             "fgd_iters_per_s": n_iter_all * a.steps / total_s,
             "mean_inner_iters": float(inner.mean()), "fulfilled_frac": float(is_[:, backend.I_FULFILLED].mean()),
-            "wall_ms_per_step": 1e3 * (wall1 - wall0) / a.steps,
+            "wall_ms_per_step": 1e3 * (wall1 - wall0) / a.steps, "step_ms": [round(m, 4) for m in step_ms],
+            "presoak_s": a.presoak_seconds,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline}
     if saturated is not None:
         line["saturated"] = saturated

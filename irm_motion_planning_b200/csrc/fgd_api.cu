@@ -48,7 +48,9 @@ inline int warps_per_trajectory(int T) { return T <= 64 ? 1 : (T <= 128 ? 2 : 4)
 // (variant, WPT, KSRC, NW, MINB): the instantiated optimiser kernels.  WPT warps per trajectory; KSRC: where the K tables
 // live - tensor memory (K_TMEM, T <= 64), shared memory (K_SMEM, T <= 64) or L2 (K_L2); NW warps per CTA (= WPT for
 // multi-warp teams), MINB = min CTAs per SM (register cap).  Variant 0 is the default; variant 1 exists for A/B
-// measurements (env FGD_VARIANT): the shared-memory tables for T <= 64.
+// measurements (env FGD_VARIANT): the shared-memory tables for T <= 64.  The TMEM kernel runs as ONE 16-warp CTA per SM:
+// cudaOccupancyMaxActiveBlocksPerMultiprocessor reported 1 CTA/SM for an 8-warp TMEM instance whose registers and shared
+// memory allow 2 (a forced grid of 2 per SM measured the same throughput as this layout).
 #define FGD_FOR_CONFIGS(X) \
     X(0, 1, K_TMEM, 16, 1) X(0, 2, K_L2, 2, 8) X(0, 4, K_L2, 4, 4) \
     X(1, 1, K_SMEM, 8, 2)
@@ -72,10 +74,6 @@ int occupancy_opt(size_t smem)
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int nb = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, NW * 32, smem) != cudaSuccess) nb = 1;
-    // kernels that allocate tensor memory: the occupancy calculator assumes one CTA per SM (it cannot know how many of
-    // the 512 columns a CTA takes); each CTA takes TMEM_COLS = 256, so MINB = 2 CTAs fit
-    if (KS == K_TMEM && nb < MINB) nb = MINB;
-    if (const char *e = std::getenv("FGD_OCC")) { const int v = std::atoi(e); if (v > 0) nb = v; }
     return nb < 1 ? 1 : nb;
 }
 

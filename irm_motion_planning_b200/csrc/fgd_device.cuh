@@ -113,13 +113,6 @@ __device__ __forceinline__ float wmax(float v)
     for (int o = 16; o >= 1; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, o));
     return v;
 }
-__device__ __forceinline__ int wmin_int(int v)
-{
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) v = min(v, __shfl_xor_sync(FULL, v, o));
-    return v;
-}
-
 // cross-warp combination of warp partials p[0..WPT-1] in butterfly order
 template <int WPT>
 __device__ __forceinline__ float combine_sum(const float *p)
@@ -370,25 +363,31 @@ __device__ __forceinline__ void contract_back_tm(unsigned tk, int T, const float
         y1[1] = fma2(kk, bc2(xa.y), y1[1]);
         y1[2] = fma2(kk, bc2(xa.z), y1[2]);
     }
-    unsigned any = nz[0][0] | nz[0][1];
-    while (any) {                                   // warp-uniform: ascending lane, then ascending r = ascending k
+    // dK (-G_v): rows 0 and T-1 carry the start/goal velocity terms in every iteration (trajectory.py:207-212), so they are
+    // visited unconditionally as straight-line code (a row that happens to be all zero adds exact zeros: fma(dv, 0, y) == y,
+    // y never being -0); the rows in between only where the velocity limit is violated.  k ascending throughout.
+    auto dk_row = [&](const int kz) {
+        unsigned r[2];
+        tmem_ld2(tk + 4 * kz + 2, r);
+        const float4 xb = xb_rows[kz];
+        tmem_wait2(r);
+        const f2 dv = u2f2(r[0], r[1]);
+        y2[0] = fma2(dv, bc2(xb.x), y2[0]);
+        y2[1] = fma2(dv, bc2(xb.y), y2[1]);
+        y2[2] = fma2(dv, bc2(xb.z), y2[2]);
+    };
+    const int lT = (T - 1) / R, rT = (T - 1) % R;
+    unsigned m0 = nz[0][0] & ~1u, m1 = nz[0][1];           // row 0 = lane 0, slot 0
+    if (rT == 0) m0 &= ~(1u << lT); else m1 &= ~(1u << lT);
+    dk_row(0);
+    unsigned any = m0 | m1;
+    while (any) {                                   // warp-uniform: ascending lane, then ascending slot = ascending k
         const int l = __ffs(any) - 1;
         any &= any - 1;
-#pragma unroll
-        for (int r_ = 0; r_ < R; ++r_) {
-            if ((nz[0][r_] >> l) & 1u) {
-                const int kz = l * R + r_;
-                unsigned r[2];
-                tmem_ld2(tk + 4 * kz + 2, r);
-                const float4 xb = xb_rows[kz];
-                tmem_wait2(r);
-                const f2 dv = u2f2(r[0], r[1]);
-                y2[0] = fma2(dv, bc2(xb.x), y2[0]);
-                y2[1] = fma2(dv, bc2(xb.y), y2[1]);
-                y2[2] = fma2(dv, bc2(xb.z), y2[2]);
-            }
-        }
+        if ((m0 >> l) & 1u) dk_row(l * R);
+        if ((m1 >> l) & 1u) dk_row(l * R + 1);
     }
+    dk_row(T - 1);
 }
 
 // ---------------------------------------------------------------------------
@@ -632,10 +631,13 @@ __device__ __forceinline__ void cost_phase(const DevParams &p, const int T, cons
     if (valid1) { part_c = part_c + cost.y; lmax = fmaxf(lmax, cost.y); }
     // max / first argmax / sums over t: inside the warp, then across the warps of the team
     float maxc = wmax(lmax);
-    int cand = 0x7fffffff;
-    if (valid1 && cost.y == maxc) cand = t0 + 1;
-    if (valid0 && cost.x == maxc) cand = t0;
-    int amax = wmin_int(cand);
+    // first sample of this warp that attains the maximum (trajectory.py:97 argmax = first index): two votes instead of a
+    // second butterfly; lane l of the warp owns the samples t0w + 2l (slot x) and t0w + 2l + 1 (slot y)
+    const unsigned bx = __ballot_sync(FULL, valid0 && cost.x == maxc), by = __ballot_sync(FULL, valid1 && cost.y == maxc);
+    const int t0w = t0 - G.lane * R;
+    int amax = 0x7fffffff;
+    if (by) amax = t0w + (__ffs(by) - 1) * R + 1;
+    if (bx) amax = min(amax, t0w + (__ffs(bx) - 1) * R);
     float sum_c = wsum(part_c), sum_p = wsum(part_p), sum_v = wsum(part_v);
     bool all_ok = __all_sync(FULL, lim_ok);
     if constexpr (WPT == 1) {

@@ -241,7 +241,7 @@ enum KSource : int { K_L2 = 0, K_SMEM = 1, K_TMEM = 2 };
 // 512 B LDS.128 per warp and k - measured ~6 data-pipe cycles - and the shared-memory pipe was the busiest unit
 // of the kernel (75 % of peak, ncu).  TMEM lane l / column 4k..4k+3 holds the same four words: one
 // tcgen05.ld.32x32b (SASS LDTM) hands every thread its entries through the tensor-memory datapath, which is not
-// the shared-memory pipe, sustains > 700 B/cycle/SM (scratch/probe_tmem.cu) and has a 12-cycle latency.  The
+// the shared-memory pipe, sustains > 700 B/cycle/SM (profiles/scripts/probe_tmem.cu) and has a 12-cycle latency.  The
 // table is written once per CTA with tcgen05.st; warp w reads the lane quadrant 32 (w % 4), so warps w and
 // w + 4 share one copy.  No tensor-core instruction is involved: the arithmetic stays FP32 FFMA2.
 // The registers of a tcgen05.ld are only valid after tcgen05.wait::ld; the wait takes them as in/out operands

@@ -1,6 +1,6 @@
 import os, sys, ctypes as C, numpy as np, torch
 sys.path.insert(0, ".")
-os.environ["FGD_LIBRARY"] = os.path.abspath("scratch/libfgd_clk.so")
+os.environ["FGD_LIBRARY"] = os.path.abspath("profiles/scripts/libfgd_clk.so")
 from irm_motion_planning_b200 import backend
 from irm_motion_planning_b200.batch import BatchedFGD
 from irm_motion_planning_b200.trajectory import Trajectory

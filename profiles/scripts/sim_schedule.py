@@ -1,9 +1,9 @@
 """What could a smarter trajectory scheduler gain on the headline batch (c2, B = 4096)?  CPU only.
 
 Iteration counts come from the C mirror oracle; the per-iteration latency of a warp as a function of the warps
-resident on its SM comes from scratch/latency.py (profiles/r01g_latency_vs_occupancy.txt).  Every SM is simulated
+resident on its SM comes from profiles/scripts/latency.py (profiles/r01g_latency_vs_occupancy.txt).  Every SM is simulated
 with W team slots; FIFO is what the persistent kernel does (global atomic queue).  Run from the repo root:
-    python scratch/sim_schedule.py [scale]        # scale = latency scale relative to the measured curve (default 1)
+    python profiles/scripts/sim_schedule.py [scale]        # scale = latency scale relative to the measured curve (default 1)
 """
 import sys
 from collections import deque

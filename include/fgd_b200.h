@@ -21,7 +21,12 @@
  *  - every function returns 0 on success, an FgdStatus code otherwise; nothing
  *    calls exit() (the reference prints "FATAL" and exit(-1), the Python host
  *    re-creates that behaviour on top of these codes).
- *  - one host thread per handle; calls on one handle are not re-entrant.
+ *  - one host thread per handle; calls on one handle are not re-entrant.  Launches
+ *    of one handle may be enqueued on different streams: every launch owns its
+ *    work-queue counter (a ring of FGD_QUEUE_RING counters), so they may overlap on
+ *    the device; at most FGD_QUEUE_RING optimise launches of one handle may be in
+ *    flight at once.  The host-buffer entry points share one staging area and are
+ *    synchronous.
  *  - all arithmetic is FP32, the reference's precision (JAX default, x64 off).
  */
 #ifndef FGD_B200_H
@@ -33,11 +38,12 @@
 extern "C" {
 #endif
 
-#define FGD_ABI_VERSION 2
+#define FGD_ABI_VERSION 3
 #define FGD_MAX_T 256            /* time samples / RKHS support points            */
 #define FGD_MAX_OUTER 16         /* length of the gd_lr table                     */
 #define FGD_FSTATE 8             /* floats of resumable state per trajectory      */
 #define FGD_ISTATE 8             /* int32s of resumable state per trajectory      */
+#define FGD_QUEUE_RING 64        /* optimise launches of one handle that may be in flight at once */
 
 typedef enum FgdStatus {
     FGD_OK = 0,
@@ -153,13 +159,24 @@ int fgd_optimize_host_io(FgdHandle *h, int32_t use_gd, int32_t B, const float *h
                          const float *h_start, const float *h_goal, float *h_fstate_out, int32_t *h_istate_out,
                          void *stream);
 
-/* Random-restart reduction: trajectories are laid out [n_problems][n_restarts];
+/* Random-restart reduction: the local trajectories are laid out [n_problems][n_restarts];
  * for each problem pick the restart with the lowest obstacle cost among the
- * constraint-fulfilling ones (falls back to lowest cost if none is fulfilled).
- * d_best_cost [n_problems], d_best_index [n_problems] = index_offset + b. */
+ * constraint-fulfilling ones (falls back to lowest cost if none is fulfilled; ties: lowest index).
+ *   global index of local trajectory (p, r) = index_offset + p * problem_stride + r
+ *     (problem_stride <= 0: n_restarts, i.e. a contiguous shard of whole problems; a shard that
+ *      holds restarts [r0, r0 + n_restarts) of EVERY problem of a sweep with R restarts passes
+ *      index_offset = r0, problem_stride = R)
+ *   d_best_cost [n_problems], d_best_index [n_problems]: may be NULL
+ *   d_best_key  [n_problems] (may be NULL): the order key as one non-negative int64,
+ *      (unfulfilled << 62) | (cost bits << 31) | global index   (cost >= 0, index < 2^31),
+ *      so that the per-problem winner over several shards is the elementwise MIN of their keys -
+ *      the payload of the sweep's single collective (fgd_key_cost / fgd_key_index decode it). */
 int fgd_argmin_per_problem(FgdHandle *h, int32_t n_problems, int32_t n_restarts, const float *d_fstate,
-                           const int32_t *d_istate, int32_t index_offset, float *d_best_cost,
-                           int32_t *d_best_index, void *stream);
+                           const int32_t *d_istate, int32_t index_offset, int32_t problem_stride, float *d_best_cost,
+                           int32_t *d_best_index, int64_t *d_best_key, void *stream);
+static inline int32_t fgd_key_index(int64_t key) { return (int32_t)(key & 0x7fffffff); }
+static inline int32_t fgd_key_fulfilled(int64_t key) { return (int32_t)(((key >> 62) & 1) ^ 1); }
+static inline uint32_t fgd_key_cost_bits(int64_t key) { return (uint32_t)((key >> 31) & 0x7fffffff); }
 
 /* Trajectory.initTrajectory (trajectory.py:73-78) on the device, for sweeps whose
  * start/goal already live in HBM.  The reference solves
@@ -183,6 +200,10 @@ int64_t fgd_zero_copy_calls(const FgdHandle *h);   /* fgd_optimize_host_io calls
 /* FP32 FFMA throughput of the current device (TFLOP/s, best of 5 launches of a
  * pure-FFMA kernel): the measured denominator of the harness's roofline.frac. */
 int fgd_measure_fp32_peak(FgdHandle *h, double *tflops_out, void *stream);
+/* MUFU.RCP throughput of the current device (10^12 reciprocals per second, best of 5 launches of
+ * a pure rcp.approx kernel): the second roofline of the obstacle stage (environment.py:43,57 -
+ * one reciprocal per (sample, obstacle) pair), nominal 148 SM x 16 / clk x 1.965 GHz = 4.65. */
+int fgd_measure_mufu_peak(FgdHandle *h, double *trcp_out, void *stream);
 int fgd_abi_version(void);
 
 #ifdef __cplusplus

@@ -15,7 +15,7 @@ import numpy as np
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FGD_LIBRARY", os.path.join(_PKG, "libfgd_b200.so"))   # override: debugging builds only
 
-FGD_ABI_VERSION = 2
+FGD_ABI_VERSION = 3
 FGD_MAX_T = 256
 FGD_MAX_OUTER = 16
 FSTATE, ISTATE = 8, 8
@@ -49,7 +49,7 @@ EXPORTED_SYMBOLS = (
     "fgd_create", "fgd_destroy", "fgd_status_string", "fgd_last_cuda_error", "fgd_set_obstacles_async",
     "fgd_obstacle_count", "fgd_eval_cost_grad", "fgd_optimize_bls", "fgd_optimize_gd", "fgd_optimize_host",
     "fgd_argmin_per_problem", "fgd_launch_geometry", "fgd_kernel_launches", "fgd_abi_version",
-    "fgd_measure_fp32_peak", "fgd_set_init_basis", "fgd_init_trajectory", "fgd_optimize_host_io", "fgd_zero_copy_calls",
+    "fgd_measure_fp32_peak", "fgd_measure_mufu_peak", "fgd_set_init_basis", "fgd_init_trajectory", "fgd_optimize_host_io", "fgd_zero_copy_calls",
 )
 
 _lib = None
@@ -80,7 +80,7 @@ def load_library(path: Optional[str] = None):
     lib.fgd_optimize_gd.argtypes = [vp, i32, fp, fp, fp, fp, ip, i32, vp]
     lib.fgd_optimize_host.argtypes = [vp, i32, i32, fp, fp, fp, fp, ip, vp]
     lib.fgd_optimize_host_io.argtypes = [vp, i32, i32, fp, fp, fp, fp, fp, ip, vp]
-    lib.fgd_argmin_per_problem.argtypes = [vp, i32, i32, fp, ip, i32, fp, ip, vp]
+    lib.fgd_argmin_per_problem.argtypes = [vp, i32, i32, fp, ip, i32, i32, fp, ip, vp, vp]
     lib.fgd_set_init_basis.argtypes = [vp, fp, fp, fp]
     lib.fgd_init_trajectory.argtypes = [vp, i32, fp, fp, fp, vp]
     lib.fgd_launch_geometry.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
@@ -89,6 +89,7 @@ def load_library(path: Optional[str] = None):
     lib.fgd_zero_copy_calls.argtypes = [vp]
     lib.fgd_zero_copy_calls.restype = C.c_int64
     lib.fgd_measure_fp32_peak.argtypes = [vp, C.POINTER(C.c_double), vp]
+    lib.fgd_measure_mufu_peak.argtypes = [vp, C.POINTER(C.c_double), vp]
     if lib.fgd_abi_version() != FGD_ABI_VERSION:
         raise RuntimeError("libfgd_b200.so ABI version mismatch; rebuild")
     if path is None:
@@ -169,6 +170,8 @@ class Handle:
         if rc:
             raise FgdError(rc, "fgd_create")
         self.T = int(cfg.n_timesteps)
+        self.obstacle_generation = 0           # bumped by every set_obstacles (callers that cache uploads compare it)
+        self._obs_keepalive = []               # sources of the most recent async uploads (a pinned source may still be in flight)
 
     def _check(self, rc: int, what: str):
         if rc:
@@ -204,7 +207,8 @@ class Handle:
                 xy = xy.numpy()
         if isinstance(xy, np.ndarray):
             xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
-        self._obs_keepalive = xy
+        self._obs_keepalive = (self._obs_keepalive + [xy])[-8:]
+        self.obstacle_generation += 1
         n = int(xy.shape[0])
         st = self._stream() if stream is None else C.c_void_p(stream)
         self._check(self._lib.fgd_set_obstacles_async(self._h, _ptr(xy), n, on_dev, st), "fgd_set_obstacles_async")
@@ -234,10 +238,11 @@ class Handle:
                                                    _ptr(start), _ptr(goal), _ptr(fstate_out), _ptr(istate_out),
                                                    self._stream()), "fgd_optimize_host_io")
 
-    def argmin_per_problem(self, n_problems, n_restarts, fstate, istate, index_offset, best_cost, best_index):
+    def argmin_per_problem(self, n_problems, n_restarts, fstate, istate, index_offset, best_cost=None, best_index=None,
+                           best_key=None, problem_stride: int = 0):
         self._check(self._lib.fgd_argmin_per_problem(self._h, n_problems, n_restarts, _ptr(fstate), _ptr(istate),
-                                                     index_offset, _ptr(best_cost), _ptr(best_index), self._stream()),
-                    "fgd_argmin_per_problem")
+                                                     index_offset, problem_stride, _ptr(best_cost), _ptr(best_index),
+                                                     _ptr(best_key), self._stream()), "fgd_argmin_per_problem")
 
     # -- device-side initTrajectory ----------------------------------------
     def set_init_basis(self, u: np.ndarray, w: np.ndarray, jinv: np.ndarray):
@@ -259,6 +264,12 @@ class Handle:
     def measure_fp32_peak(self) -> float:
         out = C.c_double()
         self._check(self._lib.fgd_measure_fp32_peak(self._h, C.byref(out), self._stream()), "fgd_measure_fp32_peak")
+        return float(out.value)
+
+    def measure_mufu_peak(self) -> float:
+        """10^12 rcp.approx per second (the obstacle stage's second roofline)."""
+        out = C.c_double()
+        self._check(self._lib.fgd_measure_mufu_peak(self._h, C.byref(out), self._stream()), "fgd_measure_mufu_peak")
         return float(out.value)
 
     def kernel_launches(self) -> int:

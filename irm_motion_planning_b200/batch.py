@@ -112,36 +112,90 @@ class BatchedFGD:
         self.handle.optimize_host_io(self.mode, B, alpha_pin, out_alpha_pin, start_pin, goal_pin, out_f_pin, out_i_pin)
 
     # -- restart sweep: local argmin + one gather ---------------------------
-    def best_per_problem(self, result: BatchResult, n_problems: int, n_restarts: int, index_offset: int = 0):
+    def best_per_problem(self, result: BatchResult, n_problems: int, n_restarts: int, index_offset: int = 0,
+                         problem_stride: int = 0):
+        """(cost [P] f32, global index [P] i32) of the best local restart of every problem."""
         import torch
         cost = torch.empty(n_problems, dtype=torch.float32, device="cuda")
         idx = torch.empty(n_problems, dtype=torch.int32, device="cuda")
-        self.handle.argmin_per_problem(n_problems, n_restarts, result.fstate, result.istate, index_offset, cost, idx)
+        self.handle.argmin_per_problem(n_problems, n_restarts, result.fstate, result.istate, index_offset, cost, idx,
+                                       problem_stride=problem_stride)
         return cost, idx
 
+    def best_keys(self, fstate, istate, n_problems: int, n_restarts: int, index_offset: int = 0, problem_stride: int = 0,
+                  out=None):
+        """Order keys [P] int64 of the best local restart of every problem (see ``decode_keys``)."""
+        import torch
+        if out is None:
+            out = torch.empty(n_problems, dtype=torch.int64, device="cuda")
+        self.handle.argmin_per_problem(n_problems, n_restarts, fstate, istate, index_offset, best_key=out,
+                                       problem_stride=problem_stride)
+        return out
 
-def gather_best(cost, idx, group=None):
-    """The single collective of a sharded sweep: all-gather the per-problem
-    (best cost, global trajectory index) pairs of every rank.  Works on CUDA
-    tensors over NCCL and on CPU tensors over gloo.  Returns concatenated
-    (cost [P_total], idx [P_total]) ordered by rank (= by problem index for
-    contiguous shards)."""
+
+# ---------------------------------------------------------------------------
+# restart sweep across ranks
+# ---------------------------------------------------------------------------
+
+def restart_shard(n_restarts: int, rank: int, world: int) -> Tuple[int, int]:
+    """Restarts [lo, hi) of EVERY problem that `rank` optimises.  Sharding the restart axis (not the problem
+    axis) gives every rank the same mix of easy and hard problems: the per-rank work differs by the sampling
+    noise of single trajectories (~0.2 % at 131 072 per rank) instead of that of whole problems (~1.5 %)."""
+    return shard_range(n_restarts, rank, world)
+
+
+def encode_keys(cost, fulfilled, index):
+    """Host/torch restatement of the argmin kernel's order key: (unfulfilled << 62) | (cost bits << 31) | index."""
+    import torch
+    cb = cost.to(torch.float32).contiguous().view(torch.int32).to(torch.int64)
+    cb = torch.where(cost >= 0, cb, torch.full_like(cb, 0x7FFFFFFF))
+    unful = (~fulfilled.to(torch.bool)).to(torch.int64)
+    return (unful << 62) | (cb << 31) | index.to(torch.int64)
+
+
+def decode_keys(keys):
+    """keys [P] int64 -> (cost f32 [P], global index i32 [P], fulfilled bool [P])."""
+    import torch
+    idx = (keys & 0x7FFFFFFF).to(torch.int32)
+    cost = ((keys >> 31) & 0x7FFFFFFF).to(torch.int32).view(torch.float32)
+    return cost, idx, ((keys >> 62) & 1) == 0
+
+
+def gather_best_keys(keys, group=None):
+    """THE collective of a restart sweep whose ranks hold different restarts of the same problems: one
+    all-gather of the per-problem order keys (8 B per problem and rank), reduced locally with an elementwise
+    minimum.  CUDA tensors over NCCL, CPU tensors over gloo.  Returns the winning keys [P] (on every rank)."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return keys
+    world = dist.get_world_size(group)
+    out = torch.empty(world * keys.numel(), dtype=torch.int64, device=keys.device)
+    dist.all_gather_into_tensor(out, keys.contiguous(), group=group)
+    return out.view(world, keys.numel()).min(dim=0).values
+
+
+def gather_best(cost, idx, n_total=None, group=None):
+    """The collective of a sweep whose ranks hold whole problems (contiguous shards, ``shard_range``): ONE
+    all-gather of the per-problem (best cost, global trajectory index) pairs.  The shard sizes follow from
+    ``shard_range(n_total, rank, world)`` on every rank - nothing is exchanged to learn them.  Works on CUDA
+    tensors over NCCL and on CPU tensors over gloo.  Returns (cost [n_total], idx [n_total]) by problem index."""
     import torch
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return cost, idx
     world = dist.get_world_size(group)
-    # shards may differ by one problem: pad to the max and trim after the gather
-    n = torch.tensor([cost.numel()], dtype=torch.int64, device=cost.device)
-    sizes = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(sizes, n, group=group)
-    sizes = [int(s.item()) for s in sizes]
+    if n_total is None:
+        n_total = cost.numel() * world              # equal shards
+    sizes = [hi - lo for lo, hi in (shard_range(n_total, r, world) for r in range(world))]
+    assert sizes[dist.get_rank(group)] == cost.numel(), "shard size does not follow shard_range(n_total, rank, world)"
     m = max(sizes)
-    packed = torch.zeros(m, 2, dtype=torch.float32, device=cost.device)
-    packed[: cost.numel(), 0] = cost
-    packed[: cost.numel(), 1] = idx.view(torch.float32) if idx.dtype == torch.int32 else idx.to(torch.int32).view(torch.float32)
-    outs = [torch.empty_like(packed) for _ in range(world)]
-    dist.all_gather(outs, packed, group=group)
-    costs = torch.cat([o[:s, 0] for o, s in zip(outs, sizes)])
-    idxs = torch.cat([o[:s, 1].contiguous().view(torch.int32) for o, s in zip(outs, sizes)])
+    packed = torch.zeros(m, 2, dtype=torch.int32, device=cost.device)       # integer container: no float canonicalisation
+    packed[: cost.numel(), 0] = cost.to(torch.float32).contiguous().view(torch.int32)
+    packed[: cost.numel(), 1] = idx.to(torch.int32)
+    out = torch.empty(world * m, 2, dtype=torch.int32, device=cost.device)
+    dist.all_gather_into_tensor(out, packed, group=group)
+    out = out.view(world, m, 2)
+    costs = torch.cat([out[r, :s, 0] for r, s in enumerate(sizes)]).contiguous().view(torch.float32)
+    idxs = torch.cat([out[r, :s, 1] for r, s in enumerate(sizes)])
     return costs, idxs

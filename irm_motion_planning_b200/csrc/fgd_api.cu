@@ -20,12 +20,12 @@ struct FgdHandle {
     float *d_init = nullptr;   // [2T + 9]: u = K^-1 1, w = K^-1 c, J^-1 (fgd_set_init_basis)
     float *d_obs[2] = {nullptr, nullptr};
     int obs_active = 0, obs_count = 0;
-    unsigned *d_queue = nullptr;
+    unsigned *d_queue = nullptr;   // FGD_QUEUE_RING work-queue counters: launch n owns counter n % FGD_QUEUE_RING
     int *h_dbg = nullptr, *d_dbg = nullptr;   // FGD_DEBUG_MARK builds: host-mapped progress markers
     cudaEvent_t obs_event = nullptr, launch_event = nullptr;
     bool obs_event_pending = false, launch_event_pending = false;
     int last_cuda_error = 0;
-    long long launches = 0, zero_copy_calls = 0;
+    long long launches = 0, zero_copy_calls = 0, opt_launches = 0;
     // scratch for the host-buffer entry point
     float *s_alpha = nullptr, *s_start = nullptr, *s_goal = nullptr, *s_fstate = nullptr;
     int *s_istate = nullptr;
@@ -215,7 +215,7 @@ void fill_params(const FgdHandle *h, DevParams &p, int mode, int B, float *alpha
     p.obs = h->d_obs[h->obs_active];
     p.alpha = alpha; p.alpha_in = alpha; p.fresh = 0;
     p.start = start; p.goal = goal; p.fstate = fstate; p.istate = istate;
-    p.queue = h->d_queue;
+    p.queue = h->d_queue + (h->opt_launches % FGD_QUEUE_RING);
     p.dbg = h->d_dbg;
 }
 
@@ -241,21 +241,29 @@ int run_optimize(FgdHandle *h, int mode, int B, float *d_alpha, const float *d_s
     fill_params(h, p, mode, B, d_alpha, d_start, d_goal, d_fstate, d_istate, budget);
     if (d_alpha_in) { p.alpha_in = d_alpha_in; p.fresh = 1; }
     const Geometry g = geometry(h, B, p.n_obs);
-    CK(cudaMemsetAsync(h->d_queue, 0, sizeof(unsigned), st));
+    CK(cudaMemsetAsync(p.queue, 0, sizeof(unsigned), st));      // this launch's own counter (launches on other streams keep theirs)
     CK(dispatch_opt(h->variant, h->WPT, h->cfg.strict_math != 0, h->cfg.whole_arm_cost != 0, p, g.grid, (size_t)g.smem, st));
     h->launches += 1;
+    h->opt_launches += 1;
     CK(cudaEventRecord(h->launch_event, st));
     h->launch_event_pending = true;
     return FGD_OK;
 }
 
-// Page-locked host memory is addressable from the device (unified addressing): returns its device alias.
-bool mapped_host_pointer(const void *p, void **dev)
+// Page-locked host memory is addressable from the device (unified addressing): returns the device alias of
+// [p, p + bytes) if the WHOLE range is page-locked and mapped contiguously (first and last byte are checked: a buffer
+// whose registration covers only part of the range must take the staged path, not fault on the device).
+bool mapped_host_range(const void *p, size_t bytes, void **dev)
 {
-    cudaPointerAttributes at;
-    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
-    if (at.type != cudaMemoryTypeHost || !at.devicePointer) return false;
-    *dev = at.devicePointer;
+    if (bytes == 0) return false;
+    cudaPointerAttributes a0, a1;
+    if (cudaPointerGetAttributes(&a0, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (a0.type != cudaMemoryTypeHost || !a0.devicePointer) return false;
+    const char *last = static_cast<const char *>(p) + (bytes - 1);
+    if (cudaPointerGetAttributes(&a1, last) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (a1.type != cudaMemoryTypeHost || !a1.devicePointer) return false;
+    if (static_cast<const char *>(a1.devicePointer) - static_cast<const char *>(a0.devicePointer) != (ptrdiff_t)(bytes - 1)) return false;
+    *dev = a0.devicePointer;
     return true;
 }
 
@@ -271,6 +279,36 @@ int ensure_scratch(FgdHandle *h, int B)
         CK(cudaMalloc(&h->s_istate, (size_t)B * FGD_ISTATE * 4));
         h->s_cap = B;
     }
+    return FGD_OK;
+}
+
+// best-of-5 throughput of a probe kernel; all resources are released on every path
+template <typename Launch>
+int measure_peak(FgdHandle *h, cudaStream_t st, double work_per_launch, Launch launch, double *out)
+{
+    float *sink = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    double best = 0.0;
+    cudaError_t err = cudaMalloc(&sink, 4);
+    if (err == cudaSuccess) err = cudaEventCreate(&e0);
+    if (err == cudaSuccess) err = cudaEventCreate(&e1);
+    for (int rep = 0; rep < 6 && err == cudaSuccess; ++rep) {          // first rep warms up, best of the rest
+        err = cudaEventRecord(e0, st);
+        if (err != cudaSuccess) break;
+        launch(1.0f + rep, sink);
+        err = cudaGetLastError();
+        if (err == cudaSuccess) err = cudaEventRecord(e1, st);
+        if (err == cudaSuccess) err = cudaEventSynchronize(e1);
+        float ms = 0.f;
+        if (err == cudaSuccess) err = cudaEventElapsedTime(&ms, e0, e1);
+        if (err == cudaSuccess && rep > 0 && ms > 0.f) { const double t = work_per_launch / (ms * 1e-3) * 1e-12; if (t > best) best = t; }
+        h->launches += 1;
+    }
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    cudaFree(sink);
+    if (err != cudaSuccess) { h->last_cuda_error = (int)err; return FGD_ERR_CUDA; }
+    *out = best;
     return FGD_OK;
 }
 
@@ -359,7 +397,7 @@ int fgd_create(const FgdConfig *cfg, FgdHandle **out)
         CKC(cudaMalloc(&h->d_obs[i], (size_t)cfg->obstacle_capacity * 2 * 4));
         CKC(cudaMemset(h->d_obs[i], 0, (size_t)cfg->obstacle_capacity * 2 * 4));
     }
-    CKC(cudaMalloc(&h->d_queue, sizeof(unsigned)));
+    CKC(cudaMalloc(&h->d_queue, FGD_QUEUE_RING * sizeof(unsigned)));
 #if defined(FGD_DEBUG_MARK) || defined(FGD_PHASE_CLOCKS)
     CKC(cudaHostAlloc(&h->h_dbg, 4096 * sizeof(int), cudaHostAllocMapped));
     std::memset(h->h_dbg, 0, 4096 * sizeof(int));
@@ -453,6 +491,8 @@ int fgd_eval_cost_grad(FgdHandle *h, int32_t B, const float *d_alpha, const floa
     const int grid = (int)(need < cap ? need : cap);
     CK(dispatch_eval(h->WPT, h->cfg.strict_math != 0, h->cfg.whole_arm_cost != 0, p, e, grid, smem, st));
     h->launches += 1;
+    CK(cudaEventRecord(h->launch_event, st));      // this kernel reads the obstacle buffer too
+    h->launch_event_pending = true;
     return FGD_OK;
 }
 
@@ -507,9 +547,10 @@ int fgd_optimize_host_io(FgdHandle *h, int32_t use_gd, int32_t B, const float *h
     {
         static const bool force_copy = [] { const char *e = std::getenv("FGD_HOST_IO"); return e && std::strcmp(e, "copy") == 0; }();
         void *d_in = nullptr, *d_out = nullptr, *d_s = nullptr, *d_g = nullptr, *d_f = nullptr, *d_i = nullptr;
-        if (!force_copy && mapped_host_pointer(h_alpha_in, &d_in) && mapped_host_pointer(h_alpha_out, &d_out) &&
-            mapped_host_pointer(h_start, &d_s) && mapped_host_pointer(h_goal, &d_g) && mapped_host_pointer(h_fstate_out, &d_f) &&
-            mapped_host_pointer(h_istate_out, &d_i)) {
+        const size_t nb_a = (size_t)B * h->T * 3 * 4, nb_sg = (size_t)B * 3 * 4;
+        if (!force_copy && mapped_host_range(h_alpha_in, nb_a, &d_in) && mapped_host_range(h_alpha_out, nb_a, &d_out) &&
+            mapped_host_range(h_start, nb_sg, &d_s) && mapped_host_range(h_goal, nb_sg, &d_g) &&
+            mapped_host_range(h_fstate_out, (size_t)B * FGD_FSTATE * 4, &d_f) && mapped_host_range(h_istate_out, (size_t)B * FGD_ISTATE * 4, &d_i)) {
             int rc = run_optimize(h, use_gd ? 1 : 0, B, (float *)d_out, (const float *)d_s, (const float *)d_g, (float *)d_f, (int *)d_i,
                                   -1, st, (const float *)d_in);
             if (rc) return rc;
@@ -534,14 +575,18 @@ int fgd_optimize_host_io(FgdHandle *h, int32_t use_gd, int32_t B, const float *h
 }
 
 int fgd_argmin_per_problem(FgdHandle *h, int32_t n_problems, int32_t n_restarts, const float *d_fstate, const int32_t *d_istate,
-                           int32_t index_offset, float *d_best_cost, int32_t *d_best_index, void *stream)
+                           int32_t index_offset, int32_t problem_stride, float *d_best_cost, int32_t *d_best_index, int64_t *d_best_key,
+                           void *stream)
 {
-    if (!h || n_problems < 0 || n_restarts < 1 || (n_problems > 0 && (!d_fstate || !d_istate || !d_best_cost || !d_best_index)))
+    if (!h || n_problems < 0 || n_restarts < 1 || (n_problems > 0 && (!d_fstate || !d_istate || (!d_best_cost && !d_best_index && !d_best_key))))
         return FGD_ERR_INVALID_ARGUMENT;
     if (n_problems == 0) return FGD_OK;
+    if (problem_stride <= 0) problem_stride = n_restarts;
+    if ((long long)index_offset + (long long)(n_problems - 1) * problem_stride + n_restarts - 1 > 0x7fffffffLL) return FGD_ERR_INVALID_ARGUMENT;
     const int block = 256, per = block / 32;
     const int grid = (n_problems + per - 1) / per;
-    fgd_argmin_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(n_problems, n_restarts, d_fstate, d_istate, index_offset, d_best_cost, d_best_index);
+    fgd_argmin_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(n_problems, n_restarts, d_fstate, d_istate, index_offset, problem_stride,
+                                                                d_best_cost, d_best_index, reinterpret_cast<long long *>(d_best_key));
     CK(cudaGetLastError());
     h->launches += 1;
     return FGD_OK;
@@ -595,27 +640,18 @@ int fgd_measure_fp32_peak(FgdHandle *h, double *tflops_out, void *stream)
 {
     if (!h || !tflops_out) return FGD_ERR_INVALID_ARGUMENT;
     cudaStream_t st = (cudaStream_t)stream;
-    float *sink = nullptr;
-    CK(cudaMalloc(&sink, 4));
-    cudaEvent_t e0, e1;
-    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     const int grid = h->num_sms * 8, iters = 4096;
-    double best = 0.0;
-    for (int rep = 0; rep < 6; ++rep) {          // first rep warms up, best of the rest
-        CK(cudaEventRecord(e0, st));
-        fgd_ffma_peak_kernel<<<grid, 256, 0, st>>>(iters, 1.0f + rep, sink);
-        CK(cudaGetLastError());
-        CK(cudaEventRecord(e1, st));
-        CK(cudaEventSynchronize(e1));
-        float ms = 0.f;
-        CK(cudaEventElapsedTime(&ms, e0, e1));
-        const double flops = (double)grid * 256 * (double)iters * 16 * 8 * 2;
-        if (rep > 0 && ms > 0.f) { const double t = flops / (ms * 1e-3) * 1e-12; if (t > best) best = t; }
-        h->launches += 1;
-    }
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
-    *tflops_out = best;
-    return FGD_OK;
+    return measure_peak(h, st, (double)grid * 256 * (double)iters * 16 * 8 * 2,
+                        [&](float seed, float *sink) { fgd_ffma_peak_kernel<<<grid, 256, 0, st>>>(iters, seed, sink); }, tflops_out);
+}
+
+int fgd_measure_mufu_peak(FgdHandle *h, double *trcp_out, void *stream)
+{
+    if (!h || !trcp_out) return FGD_ERR_INVALID_ARGUMENT;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = h->num_sms * 8, iters = 1024;
+    return measure_peak(h, st, (double)grid * 256 * (double)iters * 8 * 8,
+                        [&](float seed, float *sink) { fgd_mufu_peak_kernel<<<grid, 256, 0, st>>>(iters, seed, sink); }, trcp_out);
 }
 
 }  // extern "C"

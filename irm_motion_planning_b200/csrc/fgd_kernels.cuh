@@ -508,7 +508,8 @@ __global__ void __launch_bounds__(NW * 32) fgd_eval_kernel(const __grid_constant
 // Key order: constraint-fulfilled first, then lower obstacle cost, then lower index.
 // ---------------------------------------------------------------------------
 __global__ void fgd_argmin_kernel(int n_problems, int n_restarts, const float *__restrict__ fstate,
-                                  const int *__restrict__ istate, int index_offset, float *best_cost, int *best_index)
+                                  const int *__restrict__ istate, int index_offset, int problem_stride, float *best_cost, int *best_index,
+                                  long long *best_key)
 {
     const int lane = threadIdx.x & 31;
     const int prob = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -520,7 +521,7 @@ __global__ void fgd_argmin_kernel(int n_problems, int n_restarts, const float *_
         const unsigned ful = istate[b * FGD_ISTATE + FGD_I_FULFILLED] ? 0u : 1u;
         unsigned cb = __float_as_uint(c);
         if (!(c >= 0.0f)) cb = 0x7fffffffu;                 // NaN / negative never wins
-        const unsigned long long key = ((unsigned long long)ful << 63) | ((unsigned long long)cb << 31) | (unsigned)r;
+        const unsigned long long key = ((unsigned long long)ful << 62) | ((unsigned long long)cb << 31) | (unsigned)r;
         best = key < best ? key : best;
     }
 #pragma unroll
@@ -531,8 +532,11 @@ __global__ void fgd_argmin_kernel(int n_problems, int n_restarts, const float *_
     if (lane == 0) {
         const int r = (int)(best & 0x7fffffffu);
         const size_t b = (size_t)prob * n_restarts + r;
-        best_cost[prob] = fstate[b * FGD_FSTATE + FGD_F_TOC];
-        best_index[prob] = index_offset + (int)b;
+        const int gi = index_offset + prob * problem_stride + r;
+        if (best_cost) best_cost[prob] = fstate[b * FGD_FSTATE + FGD_F_TOC];
+        if (best_index) best_index[prob] = gi;
+        // same order key with the GLOBAL index in the low bits: the winner over several shards is the minimum key
+        if (best_key) best_key[prob] = (long long)((best & ~0x7fffffffull) | (unsigned long long)(unsigned)gi);
     }
 }
 
@@ -578,6 +582,24 @@ __global__ void __launch_bounds__(256) fgd_ffma_peak_kernel(int iters, float see
         }
     }
     const float r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (r == 123456.789f) sink[0] = r;
+}
+
+// MUFU roofline probe: 8 independent rcp.approx chains per thread (x -> 1/x -> x ...), nothing else.
+__global__ void __launch_bounds__(256) fgd_mufu_peak_kernel(int iters, float seed, float *sink)
+{
+    float a[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) a[u] = seed + 0.25f * u + 1e-3f * threadIdx.x;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) a[u] = rcp<false>(a[u]);
+        }
+    }
+    const float r = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
     if (r == 123456.789f) sink[0] = r;
 }
 

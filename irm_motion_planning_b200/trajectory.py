@@ -71,19 +71,19 @@ class Trajectory:
         return self._handle
 
     def set_obstacles(self, obstacles):
-        """Upload the obstacle set (async memcpy into the double-buffered device array)."""
+        """Upload the obstacle set (async memcpy into the double-buffered device array).  Host arrays are
+        uploaded only when their CONTENT differs from the last upload made through this method (and nobody
+        called ``handle.set_obstacles`` directly in between); tensors are always uploaded (<= 8 KB, async)."""
         import torch
         if isinstance(obstacles, torch.Tensor):
-            key = ("t", obstacles.data_ptr(), tuple(obstacles.shape), obstacles._version)
-            if key != self._obs_key:
-                self.handle.set_obstacles(obstacles)
-                self._obs_key = key
+            self.handle.set_obstacles(obstacles)
+            self._obs_key = None
             return
         arr = np.ascontiguousarray(np.asarray(obstacles, dtype=np.float32).reshape(-1, 2))
-        key = ("n", arr.tobytes())
+        key = (arr.tobytes(), self.handle.obstacle_generation)
         if key != self._obs_key:
             self.handle.set_obstacles(arr)
-            self._obs_key = key
+            self._obs_key = (key[0], self.handle.obstacle_generation)
 
     # ------------------------------------------------------------------
     def evaluate(self, alpha, kernel_matrix, jac):

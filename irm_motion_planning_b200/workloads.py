@@ -46,24 +46,39 @@ class Workload:
 
     @property
     def B(self):
-        return self.start.shape[0]
+        """trajectories of the whole workload"""
+        return self.start.shape[0] * (self.n_restarts if self.n_problems else 1)
 
 
-def _restart_alpha(traj, start, goal, n_restarts, rng, amp: float = 0.3):
+def _restart_alpha(traj, start, goal, n_restarts, rng, amp: float = 0.3, restarts=None, problems=None):
     """C5: restart r bends the straight line by a random via-offset
-    line + sin(pi c(t)) * delta, delta ~ N(0, amp^2)^3, then fits alpha like initTrajectory."""
+    line + sin(pi c(t)) * delta, delta ~ N(0, amp^2)^3, then fits alpha like initTrajectory.
+    restarts = (lo, hi) / problems = (lo, hi): generate only that block of the [P][R] sweep (a rank's shard);
+    the via-offsets are drawn for the whole sweep first, so a shard equals the same block of the full sweep."""
     P = start.shape[0]
     T = traj.N_timesteps
     delta = (rng.standard_normal((P, n_restarts, 3)) * amp).astype(np.float32)
     delta[:, 0, :] = 0.0                     # restart 0 = the plain straight line
-    s = np.repeat(start[:, None, :], n_restarts, 1).reshape(-1, 3)
-    g = np.repeat(goal[:, None, :], n_restarts, 1).reshape(-1, 3)
+    r_lo, r_hi = restarts if restarts is not None else (0, n_restarts)
+    p_lo, p_hi = problems if problems is not None else (0, P)
+    delta = delta[p_lo:p_hi, r_lo:r_hi]
+    start, goal = start[p_lo:p_hi], goal[p_lo:p_hi]
+    n_r = r_hi - r_lo
+    s = np.repeat(start[:, None, :], n_r, 1).reshape(-1, 3)
+    g = np.repeat(goal[:, None, :], n_r, 1).reshape(-1, 3)
     bump = np.sin(np.float32(np.pi) * traj.c).astype(np.float32)
-    line = s[:, None, :] + (g - s)[:, None, :] * traj.c[None, :, None] + bump[None, :, None] * delta.reshape(-1, 1, 3)
-    rhs = line @ np.linalg.inv(traj.jac).astype(np.float32)
-    B = rhs.shape[0]
-    sol = np.linalg.solve(traj.km, rhs.transpose(1, 0, 2).reshape(T, B * 3)).astype(np.float32)
-    return np.ascontiguousarray(sol.reshape(T, B, 3).transpose(1, 0, 2)), s, g
+    jinv = np.linalg.inv(traj.jac).astype(np.float32)
+    B = s.shape[0]
+    out = np.empty((B, T, 3), np.float32)
+    step = 65536                              # bounded temporaries for the 1 M sweep
+    for lo in range(0, B, step):
+        hi = min(B, lo + step)
+        line = s[lo:hi, None, :] + (g[lo:hi] - s[lo:hi])[:, None, :] * traj.c[None, :, None] \
+            + bump[None, :, None] * delta.reshape(-1, 1, 3)[lo:hi]
+        rhs = line @ jinv
+        sol = np.linalg.solve(traj.km, rhs.transpose(1, 0, 2).reshape(T, (hi - lo) * 3)).astype(np.float32)
+        out[lo:hi] = sol.reshape(T, hi - lo, 3).transpose(1, 0, 2)
+    return out, s, g
 
 
 def make_workload(name: str, B: Optional[int] = None, seed: int = 0) -> Workload:
@@ -96,10 +111,12 @@ def make_workload(name: str, B: Optional[int] = None, seed: int = 0) -> Workload
     raise ValueError(name)
 
 
-def initial_alpha(wl: Workload, traj, seed: int = 0):
-    """alpha0 [B,T,3] plus per-trajectory start/goal (expanded for C5)."""
+def initial_alpha(wl: Workload, traj, seed: int = 0, restarts=None, problems=None):
+    """alpha0 [B,T,3] plus per-trajectory start/goal (expanded for C5; `restarts` / `problems` select a
+    block of the sweep, layout [problem][restart])."""
     if wl.n_problems:
-        return _restart_alpha(traj, wl.start, wl.goal, wl.n_restarts, np.random.default_rng(seed + 1))
+        return _restart_alpha(traj, wl.start, wl.goal, wl.n_restarts, np.random.default_rng(seed + 1), restarts=restarts,
+                              problems=problems)
     return traj.initTrajectory(wl.start, wl.goal), wl.start, wl.goal
 
 

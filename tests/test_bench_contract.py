@@ -16,7 +16,7 @@ def _run(*args, timeout=240):
 
 
 def test_reference_arm_prints_the_contract_line():
-    r = _run("--impl", "reference", "--steps", "1", "--warmup", "0", "--cpu-seconds", "2", "--batch", "256")
+    r = _run("--impl", "reference", "--steps", "1", "--warmup", "0", "--cpu-seconds", "2", "--batch", "512")
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
@@ -24,7 +24,8 @@ def test_reference_arm_prints_the_contract_line():
     assert d["impl"] == "reference" and d["metric"] == "optimized trajectories/sec" and d["unit"] == "trajectories/s"
     assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["dtype"] == "f32" and d["data"] == "synthetic"
     assert d["value"] > 0 and d["steps"] == 1 and d["n_gpus"] == 1
-    assert d["config"]["workload"].startswith("c2") and "model" not in d["config"]
+    assert d["config"]["workload"].startswith("c5") and "model" not in d["config"]      # the north-star configuration by default
+    assert d["scaling"] == "strong" and d["config"]["trajectories_total"] == 512
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "oracle/fgd_mirror.c" in cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

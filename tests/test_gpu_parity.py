@@ -434,3 +434,150 @@ def test_config3_shape_subset(cuda_ready):
     a, fs, is_ = _gpu_optimize(tr, "bls", alpha0, start, goal)
     ca, cfs, cis = _mirror(args, tr, obs, "bls").optimize(alpha0, start, goal)
     assert np.array_equal(is_.cpu().numpy(), cis) and np.array_equal(a.cpu().numpy(), ca)
+
+
+def test_config3_shape_to_convergence(cuda_ready):
+    """Config 3 shape (T=256, 1024 obstacles, BLS, 4 warps per trajectory), the reference's full iteration limits
+    (200 inner x 10 outer), 64 trajectories run to convergence: bit-exact (strict)."""
+    args, tr, obs, start, goal, alpha0 = _setup(T=256, n_obs=1024, B=64, seed=11)
+    a, fs, is_ = _gpu_optimize(tr, "bls", alpha0, start, goal)
+    ca, cfs, cis = _mirror(args, tr, obs, "bls").optimize(alpha0, start, goal)
+    is_g = is_.cpu().numpy()
+    assert (is_g[:, M.I_STATUS] == M.ST_DONE).all()
+    assert is_g[:, M.I_INNER_TOTAL].mean() > 20 and is_g[:, M.I_OUTER].max() >= 2      # real runs, not a bounded prefix
+    assert np.array_equal(is_g, cis) and np.array_equal(a.cpu().numpy(), ca)
+    assert np.array_equal(fs.cpu().numpy()[:, :6], cfs[:, :6])
+
+
+def _oracle_sweep_winners(cfs, cis, P, R):
+    toc, ful = cfs[:, M.F_TOC].reshape(P, R), cis[:, M.I_FULFILLED].reshape(P, R).astype(bool)
+    c = np.where(ful, toc, np.inf)
+    c = np.where(np.isinf(c).all(1, keepdims=True), toc, c)
+    r = c.argmin(1)
+    return r, toc[np.arange(P), r], ful[np.arange(P), r]
+
+
+def test_config5_restart_sweep_pipeline_equals_oracle(cuda_ready):
+    """Config 5 end to end on a small sweep (12 problems x 32 restarts): restart inputs -> optimise (strict) ->
+    fgd_argmin_per_problem -> winners, against mirror optimise -> NumPy argmin: identical (cost, index, fulfilled).
+    Then the same sweep as two and as four restart-axis shards (what 2 / 4 ranks run), reduced by the elementwise min of
+    the order keys (what the all-gather feeds): identical winners, independent of the number of shards."""
+    import torch
+    from irm_motion_planning_b200.batch import BatchedFGD, decode_keys, restart_shard
+    from irm_motion_planning_b200.trajectory import Trajectory
+    from irm_motion_planning_b200.workloads import initial_alpha, make_workload
+    P, R = 12, 32
+    wl = make_workload("c5", B=P * R, seed=4)
+    wl.n_restarts = R                                   # same generator, fewer restarts per problem
+    tr = Trajectory(wl.args, strict_math=True)
+    tr.set_obstacles(wl.obstacles)
+    alpha0, start, goal = initial_alpha(wl, tr, 4)
+    assert alpha0.shape == (P * R, 50, 3)
+    eng = BatchedFGD(tr, "bls")
+    ca, cfs, cis = _mirror(wl.args, tr, wl.obstacles, "bls").optimize(alpha0, start, goal)
+    r_ref, c_ref, f_ref = _oracle_sweep_winners(cfs, cis, P, R)
+    assert 0 < f_ref.sum()                              # the sweep finds fulfilled winners
+
+    def run(world):
+        keys = []
+        for rank in range(world):
+            lo, hi = restart_shard(R, rank, world)
+            a_s, s_s, g_s = initial_alpha(wl, tr, 4, restarts=(lo, hi))          # a rank generates only its block
+            assert np.array_equal(a_s, alpha0.reshape(P, R, 50, 3)[:, lo:hi].reshape(-1, 50, 3))
+            a, fs, is_ = _gpu_optimize(tr, "bls", a_s, s_s, g_s)
+            keys.append(eng.best_keys(fs, is_, P, hi - lo, index_offset=lo, problem_stride=R))
+        return decode_keys(torch.stack(keys).min(dim=0).values)
+
+    for world in (1, 2, 4):
+        cost, idx, ful = run(world)
+        assert np.array_equal(idx.cpu().numpy(), np.arange(P) * R + r_ref), world
+        assert np.array_equal(cost.cpu().numpy(), c_ref), world
+        assert np.array_equal(ful.cpu().numpy(), f_ref), world
+    # (cost, index) outputs of the same kernel
+    a, fs, is_ = _gpu_optimize(tr, "bls", alpha0, start, goal)
+    c2, i2 = eng.best_per_problem(type("R", (), {"fstate": fs, "istate": is_})(), P, R)
+    assert np.array_equal(i2.cpu().numpy(), np.arange(P) * R + r_ref) and np.array_equal(c2.cpu().numpy(), c_ref)
+
+
+def test_fast_math_per_trajectory_tolerance(cuda_ready):
+    """north_star: EACH final trajectory within a stated FP32 tolerance of the reference path.  Fast mode (the product
+    default: rcp.approx, 1 ulp) against the oracle on 1024 trajectories:
+      * trajectories whose decision trace equals the oracle's (>= 90 % of them): max-abs joint-angle error <= 2e-3 rad
+        and relative obstacle-cost error <= 1e-3 for EVERY one of them;
+      * all trajectories: p99 of the joint-angle error <= 1e-1 rad, and at most 3 % outside the stated end-to-end
+        tolerance of 5e-2 rad - those are the chaotic divergences of SURVEY 0.3-3 (a 1-ulp perturbation
+        flips an Armijo / stop decision; two CPU builds of the reference differ by 3.6e-2...6.5e-2 rad the same way);
+      * same fulfilment verdict for >= 97 %; relative obstacle-cost error of the fulfilled ones: p99 <= 3e-2."""
+    args, tr, obs, start, goal, alpha0 = _setup(B=1024, strict=False, seed=33)
+    a, fs, is_ = _gpu_optimize(tr, "bls", alpha0, start, goal)
+    ca, cfs, cis = _mirror(args, tr, obs, "bls").optimize(alpha0, start, goal)
+    is_g, fs_g = is_.cpu().numpy(), fs.cpu().numpy()
+    same = is_g[:, M.I_HASH] == cis[:, M.I_HASH]
+    dq = np.abs(np.einsum("ij,bjk->bik", tr.km, a.cpu().numpy() - ca) @ tr.jac).reshape(1024, -1).max(1)
+    rel = np.abs(fs_g[:, M.F_TOC] - cfs[:, M.F_TOC]) / cfs[:, M.F_TOC]
+    both = (is_g[:, M.I_FULFILLED] == 1) & (cis[:, M.I_FULFILLED] == 1)
+    print(f"fast-math per trajectory: same trace {same.mean():.3f}; same-trace max dq {dq[same].max():.2e} max rel cost {rel[same].max():.2e}; "
+          f"all: dq p50 {np.median(dq):.2e} p99 {np.quantile(dq, 0.99):.2e} max {dq.max():.2e} outside 5e-2: {(dq > 5e-2).mean():.4f}; "
+          f"fulfilled agree {(is_g[:, M.I_FULFILLED] == cis[:, M.I_FULFILLED]).mean():.4f}; rel cost p99 (both fulfilled) {np.quantile(rel[both], 0.99):.2e}")
+    assert same.mean() >= 0.90
+    assert dq[same].max() <= 2e-3 and rel[same].max() <= 1e-3
+    assert np.quantile(dq, 0.99) <= 1e-1 and (dq > 5e-2).mean() <= 0.03
+    assert (is_g[:, M.I_FULFILLED] == cis[:, M.I_FULFILLED]).mean() >= 0.97
+    assert np.quantile(rel[both], 0.99) <= 3e-2
+
+
+@pytest.mark.parametrize("extra,series", [([], False), (["--extended-vis", "true", "--jit-loop", "false", "--strict-math", "true"], True),
+                                          (["--optimizer-name", "gd"], False), (["--batch", "40", "--n-measurements", "2"], False)])
+def test_main_report_and_output_files(cuda_ready, tmp_path, monkeypatch, capsys, extra, series):
+    """`python main.py [flags]` prints the reference's report lines (main.py:127,141-143) and writes
+    trajectory_result.txt (50 x 3) / trajectory_series.txt (N x 150) in the np.savetxt format that
+    visualization/visualization.py:91 loads with np.loadtxt."""
+    from irm_motion_planning_b200 import main as fgd_main
+    monkeypatch.chdir(tmp_path)
+    fgd_main.main(extra)
+    out = capsys.readouterr().out
+    assert "setup object, jit-compile took" in out and "took" in out
+    line = [l for l in out.splitlines() if l.startswith("result cost: ( avg")]
+    assert len(line) == 1 and "constraint fulfiled" in line[0]
+    avg, mx = float(line[0].split("avg")[1].split(",")[0]), float(line[0].split("max")[1].split(")")[0])
+    assert 1.0 < avg < mx < 3.5
+    if not extra:                                       # the default problem: the reference's own result (blog 1.69 / 2.19)
+        assert abs(avg - 1.69) < 2e-2 and abs(mx - 2.19) < 2e-2 and line[0].rstrip().endswith("True")
+        assert "ok start goal position" in out and "ok velocity limit with" in out
+    res = np.loadtxt(tmp_path / "trajectory_result.txt")
+    assert res.shape == (50, 3) and np.isfinite(res).all()
+    if not extra or series:
+        assert np.abs(res[0]).max() < 2e-2 and np.abs(res[-1] - np.array([1.2, 0.8, 0.3])).max() < 2e-2     # environment.py:14-15
+    if series:
+        ser = np.loadtxt(tmp_path / "trajectory_series.txt")
+        assert ser.ndim == 2 and ser.shape[1] == 150 and 60 <= ser.shape[0] <= 200
+        ref = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_results.npz"))["trajectory_series"]
+        assert np.abs(ser[0] - ref[0]).max() < 2e-3    # row 0 = the fitted straight line, as in the reference's file
+        assert f"({ser.shape[0]}, 50, 3)" in out        # main.py:152 prints the shape
+    else:
+        assert not (tmp_path / "trajectory_series.txt").exists()
+
+
+def test_two_streams_on_one_handle(cuda_ready):
+    """Two optimise launches of ONE handle enqueued on two streams may overlap on the device: each owns its work-queue
+    counter, so both batches are fully processed and equal the single-stream results."""
+    import torch
+    from irm_motion_planning_b200.batch import BatchedFGD
+    args, tr, obs, start, goal, alpha0 = _setup(B=3000, strict=False, seed=12)
+    eng = BatchedFGD(tr, "bls")
+    ref = [_gpu_optimize(tr, "bls", alpha0[i::2], start[i::2], goal[i::2]) for i in range(2)]
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    ins = [(torch.as_tensor(alpha0[i::2], device="cuda").clone(), torch.as_tensor(start[i::2], device="cuda").contiguous(),
+            torch.as_tensor(goal[i::2], device="cuda").contiguous(), *eng.new_state(1500)) for i in range(2)]
+    torch.cuda.synchronize()
+    for rep in range(3):
+        for i, (st, x) in enumerate(zip(streams, ins)):
+            with torch.cuda.stream(st):
+                if rep:
+                    x[3].zero_(); x[4].zero_()
+                    x[0].copy_(torch.as_tensor(alpha0[i::2], device="cuda"))
+                eng.optimize_device(*x)
+        torch.cuda.synchronize()
+        for i in range(2):
+            assert (ins[i][4][:, M.I_STATUS] == M.ST_DONE).all()
+            assert torch.equal(ins[i][0], ref[i][0]) and torch.equal(ins[i][4], ref[i][2])

@@ -44,6 +44,8 @@ extern "C" {
 #define FGD_FSTATE 8             /* floats of resumable state per trajectory      */
 #define FGD_ISTATE 8             /* int32s of resumable state per trajectory      */
 #define FGD_QUEUE_RING 64        /* optimise launches of one handle that may be in flight at once */
+#define FGD_OBS_RING 16          /* published obstacle sets kept on the device (power of two)      */
+#define FGD_SWITCH_LOG 64        /* int32 pairs per trajectory in the optional switch log of fgd_optimize_live */
 
 typedef enum FgdStatus {
     FGD_OK = 0,
@@ -108,13 +110,17 @@ const char *fgd_status_string(int status);
 int fgd_last_cuda_error(const FgdHandle *h);
 
 /* Replaces passing `self.env.obstacles` as a traced argument
- * (optimizer_BLS.py:60,79,82,90; environment.py:17-29): uploads `count` (x,y)
- * pairs into the inactive half of a double-buffered device array with
- * cudaMemcpyAsync on `stream` and makes it the active set for every launch
- * enqueued afterwards.  No recompilation, no handle re-creation.
- * xy_on_device: 0 = host pointer (pinned for true asynchrony), 1 = device. */
+ * (optimizer_BLS.py:60,79,82,90; environment.py:17-29): PUBLISHES `count` (x,y) pairs as the next obstacle
+ * generation: the set is copied (cudaMemcpyAsync on `stream`, from an internal page-locked staging copy of a host
+ * source, so the caller's buffer may be reused at once) into the next slot of a ring of FGD_OBS_RING device-resident
+ * sets, then the slot header and the "latest generation" word are updated, in stream order.  Every launch enqueued
+ * afterwards uses it; a RUNNING fgd_optimize_live kernel picks it up at its next poll.  No recompilation, no handle
+ * re-creation.  xy_on_device: 0 = host pointer, 1 = device pointer (copied device-to-device; must stay valid until
+ * the copy has run).  A slot is overwritten FGD_OBS_RING generations later; launches that captured it are waited for
+ * (stream-ordered), a running live kernel validates what it copied against the slot header instead. */
 int fgd_set_obstacles_async(FgdHandle *h, const float *xy, int32_t count, int32_t xy_on_device, void *stream);
 int fgd_obstacle_count(const FgdHandle *h);
+int fgd_obstacle_generation(const FgdHandle *h);   /* number of sets published so far (0 = the initial empty set) */
 
 /* Unit-parity hook = compute_trajectory_cost + compute_trajectory_cost_g +
  * constraintsFulfilled for B trajectories at given penalty weights
@@ -141,6 +147,22 @@ int fgd_optimize_bls(FgdHandle *h, int32_t B, float *d_alpha, const float *d_sta
                      float *d_fstate, int32_t *d_istate, int32_t max_launch_iters, void *stream);
 int fgd_optimize_gd(FgdHandle *h, int32_t B, float *d_alpha, const float *d_start, const float *d_goal,
                     float *d_fstate, int32_t *d_istate, int32_t max_launch_iters, void *stream);
+
+/* The reference's "change the environment at runtime" (README.md:25, blog-post.html:353; plain loop:
+ * optimizer_BLS.py:79,82,90 re-reads self.env.obstacles every iteration) WITHOUT leaving the kernel: same operators as
+ * fgd_optimize_bls / _gd, run to completion in ONE persistent launch while the host keeps calling
+ * fgd_set_obstacles_async on another stream.  Every trajectory team keeps a private copy of the obstacle set in shared
+ * memory and polls the "latest generation" word when it picks a trajectory up and then every `poll_every` inner
+ * iterations of that trajectory (poll_every >= 1); when the generation changed it copies the new set and re-evaluates
+ * the loss at the current alpha before the next gradient step - exactly what a relaunch with
+ * max_launch_iters = poll_every does, minus the relaunch, the state write-back / re-fetch and the host round trip.
+ * Which generation a trajectory sees at which iteration depends on timing; d_switch_log (optional, may be NULL)
+ * records it: int32 [B][FGD_SWITCH_LOG][2], entry 0 = (number of switches n, 0), entries 1..n = (inner iterations
+ * completed, generation adopted) - replaying that schedule through the budgeted entry points (or the oracle)
+ * reproduces the result bit for bit.  Single-warp teams only (n_timesteps <= 64): FGD_ERR_UNSUPPORTED_T otherwise;
+ * FGD_ERR_TOO_MANY_OBSTACLES if obstacle_capacity x teams does not fit in shared memory. */
+int fgd_optimize_live(FgdHandle *h, int32_t use_gd, int32_t B, float *d_alpha, const float *d_start, const float *d_goal,
+                      float *d_fstate, int32_t *d_istate, int32_t poll_every, int32_t *d_switch_log, void *stream);
 
 /* Same operators with HOST buffers (what a reference-side binding would call):
  * H2D of alpha/start/goal, run to completion, D2H of alpha and state, all on
@@ -170,13 +192,13 @@ int fgd_optimize_host_io(FgdHandle *h, int32_t use_gd, int32_t B, const float *h
  *   d_best_key  [n_problems] (may be NULL): the order key as one non-negative int64,
  *      (unfulfilled << 62) | (cost bits << 31) | global index   (cost >= 0, index < 2^31),
  *      so that the per-problem winner over several shards is the elementwise MIN of their keys -
- *      the payload of the sweep's single collective (fgd_key_cost / fgd_key_index decode it). */
+ *      the payload of the sweep's single collective (FGD_KEY_* decode it). */
 int fgd_argmin_per_problem(FgdHandle *h, int32_t n_problems, int32_t n_restarts, const float *d_fstate,
                            const int32_t *d_istate, int32_t index_offset, int32_t problem_stride, float *d_best_cost,
                            int32_t *d_best_index, int64_t *d_best_key, void *stream);
-static inline int32_t fgd_key_index(int64_t key) { return (int32_t)(key & 0x7fffffff); }
-static inline int32_t fgd_key_fulfilled(int64_t key) { return (int32_t)(((key >> 62) & 1) ^ 1); }
-static inline uint32_t fgd_key_cost_bits(int64_t key) { return (uint32_t)((key >> 31) & 0x7fffffff); }
+#define FGD_KEY_INDEX(key) ((int32_t)((key) & 0x7fffffff))
+#define FGD_KEY_FULFILLED(key) ((int32_t)((((key) >> 62) & 1) ^ 1))
+#define FGD_KEY_COST_BITS(key) ((uint32_t)(((key) >> 31) & 0x7fffffff))     /* IEEE-754 bits of the (non-negative) cost */
 
 /* Trajectory.initTrajectory (trajectory.py:73-78) on the device, for sweeps whose
  * start/goal already live in HBM.  The reference solves

@@ -18,6 +18,8 @@ LIB_PATH = os.environ.get("FGD_LIBRARY", os.path.join(_PKG, "libfgd_b200.so"))  
 FGD_ABI_VERSION = 3
 FGD_MAX_T = 256
 FGD_MAX_OUTER = 16
+FGD_OBS_RING = 16
+FGD_SWITCH_LOG = 64
 FSTATE, ISTATE = 8, 8
 F_LAM_SG, F_LAM_JL, F_LR, F_LOSS, F_TOC, F_LAST_NEW_LOSS = range(6)
 I_STATUS, I_OUTER, I_INNER, I_INNER_TOTAL, I_CAND_EVALS, I_ACCEPTS, I_FULFILLED, I_HASH = range(8)
@@ -47,7 +49,7 @@ class FgdConfig(C.Structure):
 
 EXPORTED_SYMBOLS = (
     "fgd_create", "fgd_destroy", "fgd_status_string", "fgd_last_cuda_error", "fgd_set_obstacles_async",
-    "fgd_obstacle_count", "fgd_eval_cost_grad", "fgd_optimize_bls", "fgd_optimize_gd", "fgd_optimize_host",
+    "fgd_obstacle_count", "fgd_obstacle_generation", "fgd_optimize_live", "fgd_eval_cost_grad", "fgd_optimize_bls", "fgd_optimize_gd", "fgd_optimize_host",
     "fgd_argmin_per_problem", "fgd_launch_geometry", "fgd_kernel_launches", "fgd_abi_version",
     "fgd_measure_fp32_peak", "fgd_measure_mufu_peak", "fgd_set_init_basis", "fgd_init_trajectory", "fgd_optimize_host_io", "fgd_zero_copy_calls",
 )
@@ -75,6 +77,8 @@ def load_library(path: Optional[str] = None):
     lib.fgd_last_cuda_error.argtypes = [vp]
     lib.fgd_set_obstacles_async.argtypes = [vp, fp, i32, i32, vp]
     lib.fgd_obstacle_count.argtypes = [vp]
+    lib.fgd_obstacle_generation.argtypes = [vp]
+    lib.fgd_optimize_live.argtypes = [vp, i32, i32, fp, fp, fp, fp, ip, i32, ip, vp]
     lib.fgd_eval_cost_grad.argtypes = [vp, i32, fp, fp, fp, f32, f32, f32, fp, fp, fp, fp, fp, ip, vp]
     lib.fgd_optimize_bls.argtypes = [vp, i32, fp, fp, fp, fp, ip, i32, vp]
     lib.fgd_optimize_gd.argtypes = [vp, i32, fp, fp, fp, fp, ip, i32, vp]
@@ -170,8 +174,7 @@ class Handle:
         if rc:
             raise FgdError(rc, "fgd_create")
         self.T = int(cfg.n_timesteps)
-        self.obstacle_generation = 0           # bumped by every set_obstacles (callers that cache uploads compare it)
-        self._obs_keepalive = []               # sources of the most recent async uploads (a pinned source may still be in flight)
+        self._obs_keepalive = []               # device-resident sources of the most recent async uploads (copied device-to-device)
 
     def _check(self, rc: int, what: str):
         if rc:
@@ -207,14 +210,19 @@ class Handle:
                 xy = xy.numpy()
         if isinstance(xy, np.ndarray):
             xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
-        self._obs_keepalive = (self._obs_keepalive + [xy])[-8:]
-        self.obstacle_generation += 1
+        if on_dev:
+            self._obs_keepalive = (self._obs_keepalive + [xy])[-FGD_OBS_RING:]      # host sources are staged inside the call
         n = int(xy.shape[0])
         st = self._stream() if stream is None else C.c_void_p(stream)
         self._check(self._lib.fgd_set_obstacles_async(self._h, _ptr(xy), n, on_dev, st), "fgd_set_obstacles_async")
 
     def obstacle_count(self) -> int:
         return int(self._lib.fgd_obstacle_count(self._h))
+
+    @property
+    def obstacle_generation(self) -> int:
+        """Number of obstacle sets published through this handle so far (callers that cache uploads compare it)."""
+        return int(self._lib.fgd_obstacle_generation(self._h))
 
     # -- evaluation --------------------------------------------------------
     def eval(self, B, alpha, start, goal, lam_sg, lam_jl, lam_max, loss=None, toc=None, grad=None, q=None, v=None,
@@ -228,6 +236,12 @@ class Handle:
         fn = self._lib.fgd_optimize_bls if mode == "bls" else self._lib.fgd_optimize_gd
         self._check(fn(self._h, B, _ptr(alpha), _ptr(start), _ptr(goal), _ptr(fstate), _ptr(istate), max_launch_iters,
                        self._stream()), f"fgd_optimize_{mode}")
+
+    def optimize_live(self, mode: str, B, alpha, start, goal, fstate, istate, poll_every: int, switch_log=None):
+        """One persistent launch that follows obstacle sets published while it runs (fgd_optimize_live)."""
+        self._check(self._lib.fgd_optimize_live(self._h, 1 if mode == "gd" else 0, B, _ptr(alpha), _ptr(start), _ptr(goal),
+                                                _ptr(fstate), _ptr(istate), int(poll_every), _ptr(switch_log), self._stream()),
+                    "fgd_optimize_live")
 
     def optimize_host(self, mode: str, B, alpha, start, goal, fstate, istate):
         self._check(self._lib.fgd_optimize_host(self._h, 1 if mode == "gd" else 0, B, _ptr(alpha), _ptr(start), _ptr(goal),

@@ -73,6 +73,7 @@ class BatchedFGD:
         self.trajectory = trajectory
         self.mode = mode
         self.T = trajectory.N_timesteps
+        self._side = None          # side stream of the live-obstacle publisher
 
     @property
     def handle(self) -> backend.Handle:
@@ -92,6 +93,35 @@ class BatchedFGD:
             fstate, istate = self.new_state(B)
         self.handle.optimize(self.mode, B, alpha, start, goal, fstate, istate, max_launch_iters)
         return BatchResult(alpha, fstate, istate)
+
+    # -- dynamic environment: one launch, obstacle sets published while it runs ---------------
+    def optimize_live(self, alpha, start, goal, fstate, istate, obstacle_sets, poll_every: int = 8, period_us: float = 200.0,
+                      switch_log=None, max_sets: Optional[int] = None) -> int:
+        """Config 4 without relaunches: ONE persistent launch on the current stream; meanwhile this thread publishes
+        ``obstacle_sets[k % len]`` (host arrays or pinned tensors) every ``period_us`` on a side stream with
+        ``fgd_set_obstacles_async`` until the launch has finished (or ``max_sets`` were published).  Every team polls the
+        generation counter when it picks a trajectory up and every ``poll_every`` inner iterations.  Returns the number
+        of sets published.  The call returns when the kernel has finished (the host is the publisher)."""
+        import time
+        import torch
+        B = int(alpha.shape[0])
+        h = self.handle
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+        done = torch.cuda.Event()
+        h.optimize_live(self.mode, B, alpha, start, goal, fstate, istate, poll_every, switch_log)
+        done.record()
+        k, side = 0, self._side.cuda_stream
+        t_next = time.perf_counter()
+        while not done.query() and (max_sets is None or k < max_sets):
+            now = time.perf_counter()
+            if now < t_next:
+                continue
+            t_next = now + period_us * 1e-6
+            k += 1
+            h.set_obstacles(obstacle_sets[k % len(obstacle_sets)], stream=side)
+        done.synchronize()
+        return k
 
     # -- host-buffer path (what the reference-facing call looks like) -----
     def optimize_host(self, alpha: np.ndarray, start: np.ndarray, goal: np.ndarray) -> BatchResult:

@@ -18,8 +18,15 @@ struct FgdHandle {
     int device, num_sms, max_smem_optin;
     float *d_KD = nullptr, *d_KO = nullptr;
     float *d_init = nullptr;   // [2T + 9]: u = K^-1 1, w = K^-1 c, J^-1 (fgd_set_init_basis)
-    float *d_obs[2] = {nullptr, nullptr};
-    int obs_active = 0, obs_count = 0;
+    // obstacle ring: generation g lives in slot g % FGD_OBS_RING (fgd_set_obstacles_async)
+    float *d_obs_ring = nullptr;           // [FGD_OBS_RING][capacity][2]
+    int *d_obs_meta = nullptr;             // [0] latest generation, [2 + 2s], [3 + 2s]: generation / count of slot s
+    float *h_obs_stage = nullptr;          // page-locked staging copies of host sources, one per slot
+    int *h_meta_stage = nullptr;           // page-locked sources of the header copies: per slot {-1, gen, count, gen}
+    cudaEvent_t stage_event[FGD_OBS_RING] = {};
+    bool stage_pending[FGD_OBS_RING] = {};
+    bool slot_captured[FGD_OBS_RING] = {}; // a launch enqueued since the slot was written reads it
+    int obs_gen = 0, obs_count = 0;
     unsigned *d_queue = nullptr;   // FGD_QUEUE_RING work-queue counters: launch n owns counter n % FGD_QUEUE_RING
     int *h_dbg = nullptr, *d_dbg = nullptr;   // FGD_DEBUG_MARK builds: host-mapped progress markers
     cudaEvent_t obs_event = nullptr, launch_event = nullptr;
@@ -191,13 +198,13 @@ cudaError_t dispatch_eval(int WPT, bool strict, bool arm, const DevParams &p, co
     return cudaErrorInvalidValue;
 }
 
-Geometry geometry(const FgdHandle *h, int B, int n_obs)
+Geometry geometry(const FgdHandle *h, int B, int n_obs, bool live = false)
 {
     Geometry g;
     const int nw = warps_per_cta(h->variant, h->WPT);
     const int teams = nw / h->WPT;
     g.block = nw * 32;
-    g.smem = (int)make_layout(h->T, h->TP, n_obs, k_source(h->variant, h->WPT), teams, h->WPT).bytes();
+    g.smem = (int)make_layout(h->T, h->TP, live ? h->cfg.obstacle_capacity : n_obs, k_source(h->variant, h->WPT), teams, h->WPT, live).bytes();
     const int occ = dispatch_occ(h->variant, h->WPT, h->T, h->cfg.strict_math != 0, h->cfg.whole_arm_cost != 0, (size_t)g.smem);
     const long long need = ((long long)B + teams - 1) / teams;
     const long long cap = (long long)occ * h->num_sms;
@@ -212,7 +219,9 @@ void fill_params(const FgdHandle *h, DevParams &p, int mode, int B, float *alpha
     p = h->base;
     p.mode = mode; p.B = B; p.budget = budget;
     p.n_obs = h->obs_count;
-    p.obs = h->d_obs[h->obs_active];
+    p.obs = h->d_obs_ring + (size_t)(h->obs_gen % FGD_OBS_RING) * h->cfg.obstacle_capacity * 2;
+    p.obs_meta = h->d_obs_meta; p.obs_ring = h->d_obs_ring; p.obs_cap = h->cfg.obstacle_capacity;
+    p.poll_every = 0; p.switch_log = nullptr;
     p.alpha = alpha; p.alpha_in = alpha; p.fresh = 0;
     p.start = start; p.goal = goal; p.fstate = fstate; p.istate = istate;
     p.queue = h->d_queue + (h->opt_launches % FGD_QUEUE_RING);
@@ -230,7 +239,7 @@ int wait_obstacles(FgdHandle *h, cudaStream_t st)
 // d_alpha_in != nullptr: a fresh run that reads the initial alpha rows from d_alpha_in, writes the results to d_alpha
 // and never reads the loop state (fgd_optimize_host_io).
 int run_optimize(FgdHandle *h, int mode, int B, float *d_alpha, const float *d_start, const float *d_goal, float *d_fstate,
-                 int *d_istate, int budget, cudaStream_t st, const float *d_alpha_in = nullptr)
+                 int *d_istate, int budget, cudaStream_t st, const float *d_alpha_in = nullptr, int poll_every = 0, int *d_switch_log = nullptr)
 {
     if (!h || B < 0 || (B > 0 && (!d_alpha || !d_start || !d_goal || !d_fstate || !d_istate))) return FGD_ERR_INVALID_ARGUMENT;
     if (mode == 1 && h->cfg.max_outer_iteration > h->cfg.n_gd_lr) return FGD_ERR_INVALID_ARGUMENT;   // optimizer_GD.py:34-36
@@ -240,13 +249,22 @@ int run_optimize(FgdHandle *h, int mode, int B, float *d_alpha, const float *d_s
     DevParams p;
     fill_params(h, p, mode, B, d_alpha, d_start, d_goal, d_fstate, d_istate, budget);
     if (d_alpha_in) { p.alpha_in = d_alpha_in; p.fresh = 1; }
-    const Geometry g = geometry(h, B, p.n_obs);
+    const bool live = poll_every > 0;
+    if (live) {
+        if (h->WPT != 1) return FGD_ERR_UNSUPPORTED_T;
+        p.poll_every = poll_every; p.switch_log = d_switch_log;
+    }
+    const Geometry g = geometry(h, B, p.n_obs, live);
+    if (g.smem + 64 > h->max_smem_optin) return FGD_ERR_TOO_MANY_OBSTACLES;
     CK(cudaMemsetAsync(p.queue, 0, sizeof(unsigned), st));      // this launch's own counter (launches on other streams keep theirs)
     CK(dispatch_opt(h->variant, h->WPT, h->cfg.strict_math != 0, h->cfg.whole_arm_cost != 0, p, g.grid, (size_t)g.smem, st));
     h->launches += 1;
     h->opt_launches += 1;
-    CK(cudaEventRecord(h->launch_event, st));
-    h->launch_event_pending = true;
+    if (!live) {        // a live kernel copies what it needs and validates it against the slot header; it must not hold up the publisher
+        CK(cudaEventRecord(h->launch_event, st));
+        h->launch_event_pending = true;
+        h->slot_captured[h->obs_gen % FGD_OBS_RING] = true;
+    }
     return FGD_OK;
 }
 
@@ -393,9 +411,17 @@ int fgd_create(const FgdConfig *cfg, FgdHandle **out)
     CKC(cudaMemcpy(h->d_KD, kd.data(), kd.size() * 4, cudaMemcpyHostToDevice));
     CKC(cudaMalloc(&h->d_KO, ko.size() * 4));
     CKC(cudaMemcpy(h->d_KO, ko.data(), ko.size() * 4, cudaMemcpyHostToDevice));
-    for (int i = 0; i < 2; ++i) {
-        CKC(cudaMalloc(&h->d_obs[i], (size_t)cfg->obstacle_capacity * 2 * 4));
-        CKC(cudaMemset(h->d_obs[i], 0, (size_t)cfg->obstacle_capacity * 2 * 4));
+    {
+        const size_t slot = (size_t)cfg->obstacle_capacity * 2 * 4;
+        CKC(cudaMalloc(&h->d_obs_ring, FGD_OBS_RING * slot));
+        CKC(cudaMemset(h->d_obs_ring, 0, FGD_OBS_RING * slot));
+        std::vector<int> meta(2 + 2 * FGD_OBS_RING, -1);       // generation 0 = the empty set in slot 0
+        meta[0] = 0; meta[1] = 0; meta[2] = 0; meta[3] = 0;
+        CKC(cudaMalloc(&h->d_obs_meta, meta.size() * 4));
+        CKC(cudaMemcpy(h->d_obs_meta, meta.data(), meta.size() * 4, cudaMemcpyHostToDevice));
+        CKC(cudaHostAlloc(&h->h_obs_stage, FGD_OBS_RING * slot, cudaHostAllocDefault));
+        CKC(cudaHostAlloc(&h->h_meta_stage, FGD_OBS_RING * 4 * sizeof(int), cudaHostAllocDefault));
+        for (int i = 0; i < FGD_OBS_RING; ++i) CKC(cudaEventCreateWithFlags(&h->stage_event[i], cudaEventDisableTiming));
     }
     CKC(cudaMalloc(&h->d_queue, FGD_QUEUE_RING * sizeof(unsigned)));
 #if defined(FGD_DEBUG_MARK) || defined(FGD_PHASE_CLOCKS)
@@ -443,7 +469,10 @@ int fgd_destroy(FgdHandle *h)
 {
     if (!h) return FGD_OK;
     cudaFree(h->d_init);
-    cudaFree(h->d_KD); cudaFree(h->d_KO); cudaFree(h->d_obs[0]); cudaFree(h->d_obs[1]); cudaFree(h->d_queue);
+    cudaFree(h->d_KD); cudaFree(h->d_KO); cudaFree(h->d_obs_ring); cudaFree(h->d_obs_meta); cudaFree(h->d_queue);
+    if (h->h_obs_stage) cudaFreeHost(h->h_obs_stage);
+    if (h->h_meta_stage) cudaFreeHost(h->h_meta_stage);
+    for (int i = 0; i < FGD_OBS_RING; ++i) if (h->stage_event[i]) cudaEventDestroy(h->stage_event[i]);
     cudaFree(h->s_alpha); cudaFree(h->s_start); cudaFree(h->s_goal); cudaFree(h->s_fstate); cudaFree(h->s_istate);
     if (h->obs_event) cudaEventDestroy(h->obs_event);
     if (h->launch_event) cudaEventDestroy(h->launch_event);
@@ -456,19 +485,40 @@ int fgd_set_obstacles_async(FgdHandle *h, const float *xy, int32_t count, int32_
     if (!h || count < 0 || (count > 0 && !xy)) return FGD_ERR_INVALID_ARGUMENT;
     if (count > h->cfg.obstacle_capacity) return FGD_ERR_TOO_MANY_OBSTACLES;
     cudaStream_t st = (cudaStream_t)stream;
-    const int next = h->obs_active ^ 1;
-    // the half being overwritten may still be read by the launch before the previous swap
-    if (h->launch_event_pending) CK(cudaStreamWaitEvent(st, h->launch_event, 0));
-    if (count > 0)
-        CK(cudaMemcpyAsync(h->d_obs[next], xy, (size_t)count * 2 * 4, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    const int gen = h->obs_gen + 1, s = gen % FGD_OBS_RING;
+    const size_t slot_floats = (size_t)h->cfg.obstacle_capacity * 2;
+    // the staging copies of this slot were last used FGD_OBS_RING generations ago
+    if (h->stage_pending[s]) { CK(cudaEventSynchronize(h->stage_event[s])); h->stage_pending[s] = false; }
+    // a launch that captured this slot may not have run yet (live kernels validate against the slot header instead)
+    if (h->slot_captured[s] && h->launch_event_pending) CK(cudaStreamWaitEvent(st, h->launch_event, 0));
+    h->slot_captured[s] = false;
+    int *ms = h->h_meta_stage + 4 * s;
+    ms[0] = -1; ms[1] = gen; ms[2] = count; ms[3] = gen;
+    int *meta = h->d_obs_meta;
+    float *dst = h->d_obs_ring + (size_t)s * slot_floats;
+    CK(cudaMemcpyAsync(meta + 2 + 2 * s, ms, 4, cudaMemcpyHostToDevice, st));                    // header := invalid
+    if (count > 0) {
+        if (on_device) {
+            CK(cudaMemcpyAsync(dst, xy, (size_t)count * 8, cudaMemcpyDeviceToDevice, st));
+        } else {
+            float *stage = h->h_obs_stage + (size_t)s * slot_floats;
+            std::memcpy(stage, xy, (size_t)count * 8);                                          // the caller's buffer is free again
+            CK(cudaMemcpyAsync(dst, stage, (size_t)count * 8, cudaMemcpyHostToDevice, st));
+        }
+    }
+    CK(cudaMemcpyAsync(meta + 2 + 2 * s, ms + 1, 8, cudaMemcpyHostToDevice, st));                // header := (gen, count)
+    CK(cudaMemcpyAsync(meta, ms + 3, 4, cudaMemcpyHostToDevice, st));                            // latest := gen
+    CK(cudaEventRecord(h->stage_event[s], st));
+    h->stage_pending[s] = true;
     CK(cudaEventRecord(h->obs_event, st));
     h->obs_event_pending = true;
-    h->obs_active = next;
+    h->obs_gen = gen;
     h->obs_count = count;
     return FGD_OK;
 }
 
 int fgd_obstacle_count(const FgdHandle *h) { return h ? h->obs_count : -1; }
+int fgd_obstacle_generation(const FgdHandle *h) { return h ? h->obs_gen : -1; }
 
 int fgd_eval_cost_grad(FgdHandle *h, int32_t B, const float *d_alpha, const float *d_start, const float *d_goal,
                        float lambda_sg, float lambda_jl, float lambda_max_cost, float *d_loss, float *d_toc, float *d_grad,
@@ -491,8 +541,9 @@ int fgd_eval_cost_grad(FgdHandle *h, int32_t B, const float *d_alpha, const floa
     const int grid = (int)(need < cap ? need : cap);
     CK(dispatch_eval(h->WPT, h->cfg.strict_math != 0, h->cfg.whole_arm_cost != 0, p, e, grid, smem, st));
     h->launches += 1;
-    CK(cudaEventRecord(h->launch_event, st));      // this kernel reads the obstacle buffer too
+    CK(cudaEventRecord(h->launch_event, st));      // this kernel reads the obstacle ring too
     h->launch_event_pending = true;
+    h->slot_captured[h->obs_gen % FGD_OBS_RING] = true;
     return FGD_OK;
 }
 
@@ -506,6 +557,14 @@ int fgd_optimize_gd(FgdHandle *h, int32_t B, float *d_alpha, const float *d_star
                     int32_t *d_istate, int32_t max_launch_iters, void *stream)
 {
     return run_optimize(h, 1, B, d_alpha, d_start, d_goal, d_fstate, d_istate, max_launch_iters, (cudaStream_t)stream);
+}
+
+int fgd_optimize_live(FgdHandle *h, int32_t use_gd, int32_t B, float *d_alpha, const float *d_start, const float *d_goal,
+                      float *d_fstate, int32_t *d_istate, int32_t poll_every, int32_t *d_switch_log, void *stream)
+{
+    if (poll_every < 1) return FGD_ERR_INVALID_ARGUMENT;
+    return run_optimize(h, use_gd ? 1 : 0, B, d_alpha, d_start, d_goal, d_fstate, d_istate, -1, (cudaStream_t)stream, nullptr, poll_every,
+                        d_switch_log);
 }
 
 int fgd_optimize_host(FgdHandle *h, int32_t use_gd, int32_t B, float *h_alpha, const float *h_start, const float *h_goal,

@@ -54,6 +54,11 @@ struct DevParams {
     int *istate;
     unsigned *queue;
     int *dbg;                // optional host-mapped progress markers (debug builds only)
+    // live obstacle updates (fgd_optimize_live, poll_every > 0): the ring of published obstacle sets
+    const int *obs_meta;     // [0]: latest published generation; [2 + 2s], [3 + 2s]: generation and count held by ring slot s
+    const float *obs_ring;   // [FGD_OBS_RING][obs_cap][2]
+    int obs_cap, poll_every;
+    int *switch_log;         // optional [B][FGD_SWITCH_LOG][2]
 };
 
 struct EvalPtrs {
@@ -554,7 +559,7 @@ __device__ __forceinline__ void obstacle_block(const float2 *__restrict__ obs, c
 // 0.8 and -0.8 of environment.py:43,57 (times 2 and 4) are applied once per sample.
 // ---------------------------------------------------------------------------
 template <int WPT, bool STRICT, bool ARM>
-__device__ __forceinline__ void cost_phase(const DevParams &p, const int T, const float2 *__restrict__ sObs, const Team<WPT> &G,
+__device__ __forceinline__ void cost_phase(const DevParams &p, const int T, const float2 *__restrict__ sObs, const int n_obs, const Team<WPT> &G,
                                            const f2 (&yq)[3], const f2 (&yv)[3],
                                            const float *start, const float *goal, float lam_sg, float lam_jl,
                                            Rows<ARM> &Rw, float &loss, float &toc, int &ful)
@@ -606,7 +611,6 @@ __device__ __forceinline__ void cost_phase(const DevParams &p, const int T, cons
     f2 sr[NJ], sx[NJ], sy[NJ];
 #pragma unroll
     for (int j = 0; j < NJ; ++j) { sr[j] = bc2(0.0f); sx[j] = bc2(0.0f); sy[j] = bc2(0.0f); }
-    const int n_obs = p.n_obs;
     int o = 0;
 #pragma unroll 1
     for (; o + 4 <= n_obs; o += 4) {

@@ -27,19 +27,22 @@ namespace fgd {
 // shared-memory carve-up, identical on host and device
 struct SmemLayout {
     int k_floats;     // T*TP when the K tables are staged in shared memory (KD = 2x, KO = 1x), 0 when they stay in L2
-    int obs_pairs;    // obstacle slots (padded to even)
+    int obs_pairs;    // obstacle slots of one copy of the obstacle set (padded to even)
+    int obs_copies;   // 1: one copy per CTA; n_teams: a private copy per team (live obstacle updates)
     int x_rows;       // float4 rows per operand buffer
     int n_teams;      // trajectory teams per CTA
     int xch_words;    // exchange scratch words per team (0 for single-warp teams)
     __host__ __device__ size_t team_bytes() const { return (size_t)2 * x_rows * 16 + (size_t)xch_words * 4; }
-    __host__ __device__ size_t bytes() const { return (size_t)3 * k_floats * 4 + (size_t)obs_pairs * 8 + (size_t)n_teams * team_bytes(); }
+    __host__ __device__ size_t bytes() const { return (size_t)3 * k_floats * 4 + (size_t)obs_copies * obs_pairs * 8 + (size_t)n_teams * team_bytes(); }
 };
 
-__host__ __device__ inline SmemLayout make_layout(int T, int TP, int n_obs, int ksrc, int n_teams, int wpt)
+// n_obs: obstacles of the launch; live launches size every team's private copy for the capacity instead
+__host__ __device__ inline SmemLayout make_layout(int T, int TP, int n_obs, int ksrc, int n_teams, int wpt, bool per_team_obs = false)
 {
     SmemLayout l;
     l.k_floats = ksrc == K_SMEM ? T * TP : 0;
     l.obs_pairs = (n_obs + 2) & ~1;
+    l.obs_copies = per_team_obs ? n_teams : 1;
     l.x_rows = T | 1;     // odd row count: the operand buffers of neighbouring teams start 4 banks apart (mod 8)
     l.n_teams = n_teams;
     l.xch_words = wpt > 1 ? XCH_WORDS : 0;
@@ -152,7 +155,8 @@ __device__ __forceinline__ void fetch_slot(const DevParams &p, const Team<WPT> &
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
 template <int KS>
-__device__ __forceinline__ void stage_constants(const DevParams &p, const SmemLayout &L, float *sKD, float *sKO, float2 *sObs, int nthreads)
+__device__ __forceinline__ void stage_constants(const DevParams &p, const SmemLayout &L, float *sKD, float *sKO, float2 *sObs, int nthreads,
+                                                bool stage_obs = true)
 {
     __shared__ __align__(8) unsigned long long tma_bar;
     if constexpr (KS == K_SMEM) {
@@ -173,7 +177,7 @@ __device__ __forceinline__ void stage_constants(const DevParams &p, const SmemLa
     }
     // trip counts are CTA-uniform (the bound check is inside), so no warp diverges ahead of the barrier
 #pragma unroll 1
-    for (int i0 = 0; i0 < L.obs_pairs; i0 += nthreads) {
+    for (int i0 = 0; stage_obs && i0 < L.obs_pairs; i0 += nthreads) {
         const int i = i0 + threadIdx.x;
         if (i < L.obs_pairs) sObs[i] = (i < p.n_obs) ? make_float2(p.obs[2 * i], p.obs[2 * i + 1]) : make_float2(0.f, 0.f);
     }
@@ -229,6 +233,62 @@ __device__ __forceinline__ void tmem_release_tables(unsigned tk)
 }
 
 // ---------------------------------------------------------------------------
+// Live obstacle updates (fgd_optimize_live; single-warp teams).  The host publishes obstacle generation g into ring slot
+// g % FGD_OBS_RING with stream-ordered copies: slot header := -1, data, slot header := (g, count), latest := g.  A team
+// adopts the latest generation seqlock-style: header == g before and after its copy into the team's private shared-memory
+// set, otherwise it retries with whatever is latest by then.  All ring reads bypass L1 (a slot is rewritten while the
+// kernel runs).  Returns true when the team's set changed.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int ld_acquire_sys(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float2 ld_volatile_f2(const float2 *p)
+{
+    float2 v;
+    asm volatile("ld.volatile.global.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ bool live_refresh(const DevParams &p, const int lane, float2 *sObsT, int &cur_gen, int &n_obs)
+{
+    bool changed = false;
+    for (;;) {
+        int gen = 0, hdr = 0, cnt = 0;
+        if (lane == 0) gen = ld_acquire_sys(p.obs_meta);
+        gen = __shfl_sync(FULL, gen, 0);
+        if (gen == cur_gen) return changed;
+        const int s = gen & (FGD_OBS_RING - 1);
+        if (lane == 0) { hdr = ld_acquire_sys(p.obs_meta + 2 + 2 * s); cnt = ld_acquire_sys(p.obs_meta + 3 + 2 * s); }
+        hdr = __shfl_sync(FULL, hdr, 0); cnt = __shfl_sync(FULL, cnt, 0);
+        if (hdr != gen || cnt < 0 || cnt > p.obs_cap) continue;        // the slot is being rewritten: a newer generation is on its way
+        const float2 *src = reinterpret_cast<const float2 *>(p.obs_ring) + (size_t)s * p.obs_cap;
+        const int pairs = (cnt + 2) & ~1;
+        __syncwarp();                                                 // nobody of the team still reads the old set
+        for (int i = lane; i < pairs; i += 32) sObsT[i] = i < cnt ? ld_volatile_f2(src + i) : make_float2(0.f, 0.f);
+        __syncwarp();                                                 // every lane's ring reads have returned (their values are in shared memory)
+        if (lane == 0) hdr = ld_acquire_sys(p.obs_meta + 2 + 2 * s);
+        hdr = __shfl_sync(FULL, hdr, 0);
+        if (hdr != gen) continue;                                      // overwritten while copying
+        cur_gen = gen; n_obs = cnt; changed = true;
+        return true;
+    }
+}
+
+// switch log of trajectory b: entry 0 = (count, 0), entries 1..count = (inner iterations completed, generation adopted)
+__device__ __forceinline__ void log_switch(const DevParams &p, const int lane, const int traj, int &n_switch, const int inner_total, const int gen)
+{
+    n_switch += 1;
+    if (p.switch_log && lane == 0) {
+        int *row = p.switch_log + (size_t)traj * FGD_SWITCH_LOG * 2;
+        row[0] = n_switch; row[1] = 0;
+        if (n_switch < FGD_SWITCH_LOG) { row[2 * n_switch] = inner_total; row[2 * n_switch + 1] = gen; }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // Persistent optimiser: every team of WPT warps runs one trajectory as an
 // autonomous state machine and keeps pulling trajectories until the batch queue
 // is empty.  One loop trip = one contraction + the post-processing of its result
@@ -247,14 +307,16 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int TEAMS = NW / WPT;
     const int T = TC > 0 ? TC : p.T;
-    const SmemLayout L = make_layout(T, WPT * 32 * R, p.n_obs, KS, TEAMS, WPT);
+    const bool live = WPT == 1 && p.poll_every > 0;            // live obstacle updates: a private obstacle set per team
+    const SmemLayout L = make_layout(T, WPT * 32 * R, live ? p.obs_cap : p.n_obs, KS, TEAMS, WPT, live);
     float *sKD = reinterpret_cast<float *>(smem_raw);
     float *sKO = sKD + 2 * L.k_floats;
     float2 *sObs = reinterpret_cast<float2 *>(sKO + L.k_floats);
-    unsigned char *sTeams = reinterpret_cast<unsigned char *>(sObs + L.obs_pairs);
-    stage_constants<KS>(p, L, sKD, sKO, sObs, NW * 32);
+    unsigned char *sTeams = reinterpret_cast<unsigned char *>(sObs + (size_t)L.obs_copies * L.obs_pairs);
+    stage_constants<KS>(p, L, sKD, sKO, sObs, NW * 32, !live);
 
     const int team = (threadIdx.x >> 5) / WPT;
+    if (live) sObs += (size_t)team * L.obs_pairs;
     float4 *XA = reinterpret_cast<float4 *>(sTeams + (size_t)team * L.team_bytes()), *XB = XA + L.x_rows;
     const Team<WPT> G(reinterpret_cast<float *>(XB + L.x_rows));
     const float *kd = (KS == K_SMEM ? sKD : p.KD) + G.tl * 2 * R;
@@ -262,6 +324,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
     unsigned tk = 0;
     if constexpr (KS == K_TMEM) tk = tmem_stage_tables(p);
     (void)kd; (void)ko; (void)tk;
+    int n_obs = p.n_obs, cur_gen = -1, polled_at = -1, n_switch = 0;      // live: the team's obstacle set and poll bookkeeping
+    (void)cur_gen; (void)polled_at; (void)n_switch;
 
     int kind = K_IDLE;
     Slot st;                   // team-uniform loop state of this team's trajectory (registers)
@@ -329,7 +393,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
             Rows<ARM> Rw;
             float loss_c, toc_c;
             int ful_c;
-            cost_phase<WPT, STRICT, ARM>(p, T, sObs, G, y1, y2, st.start, st.goal, st.lam_sg, st.lam_jl, Rw, loss_c, toc_c, ful_c);
+            cost_phase<WPT, STRICT, ARM>(p, T, sObs, n_obs, G, y1, y2, st.start, st.goal, st.lam_sg, st.lam_jl, Rw, loss_c, toc_c, ful_c);
             PCLK(1);
             bool accept = false;
             if (kind == K_EVAL0) {
@@ -379,7 +443,18 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
         bool save_active = false;
         if (want_head) {                                         // optimizer_BLS.py:155-157
             if (st.inner < p.max_inner) {
-                if (p.budget >= 0 && st.done_iters == p.budget) save_active = true;
+                bool switched = false;
+                if constexpr (WPT == 1) {
+                    // live obstacle updates: every poll_every inner iterations of this trajectory look for a newer obstacle set
+                    // (plain-loop semantics, optimizer_BLS.py:79,82,90: the environment is re-read between iterations)
+                    if (live && st.inner_total != polled_at && st.inner_total % p.poll_every == 0) {
+                        polled_at = st.inner_total;
+                        switched = live_refresh(p, G.lane, sObs, cur_gen, n_obs);
+                        if (switched) log_switch(p, G.lane, st.traj, n_switch, st.inner_total, cur_gen);
+                    }
+                }
+                if (switched) want_eval = true;                  // like a resumed launch: the loss at the new obstacle set first
+                else if (p.budget >= 0 && st.done_iters == p.budget) save_active = true;
                 else { st.done_iters += 1; st.inner_total += 1; kind = K_BACK; }
             } else {
                 want_end = true;
@@ -404,6 +479,13 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
             if (!boot) save_slot<WPT>(p, G, st, retire ? FGD_ST_DONE : FGD_ST_ACTIVE, a, reinterpret_cast<float *>(XA));
             fetch_slot<WPT, MODE>(p, G, st, kind, a, reinterpret_cast<float *>(XA));
             want_eval = (kind != K_IDLE);
+            if constexpr (WPT == 1) {
+                if (live && kind != K_IDLE) {                  // a trajectory starts with the latest obstacle set
+                    live_refresh(p, G.lane, sObs, cur_gen, n_obs);
+                    n_switch = 0; polled_at = st.inner_total;
+                    log_switch(p, G.lane, st.traj, n_switch, st.inner_total, cur_gen);
+                }
+            }
         }
         if (want_eval) {
             // (re)start with the loss and gradient operands at the current alpha: optimizer_BLS.py:163, optimizer_GD.py:210
@@ -469,7 +551,7 @@ __global__ void __launch_bounds__(NW * 32) fgd_eval_kernel(const __grid_constant
         Rows<ARM> Rw;
         float loss, toc;
         int ful;
-        cost_phase<WPT, STRICT, ARM>(p, T, sObs, G, y1, y2, start, goal, e.lam_sg, e.lam_jl, Rw, loss, toc, ful);
+        cost_phase<WPT, STRICT, ARM>(p, T, sObs, p.n_obs, G, y1, y2, start, goal, e.lam_sg, e.lam_jl, Rw, loss, toc, ful);
         if (G.tl == 0) {
             if (e.loss) e.loss[b] = loss;
             if (e.toc) e.toc[b] = toc;

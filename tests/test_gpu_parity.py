@@ -467,8 +467,8 @@ def test_config5_restart_sweep_pipeline_equals_oracle(cuda_ready):
     from irm_motion_planning_b200.trajectory import Trajectory
     from irm_motion_planning_b200.workloads import initial_alpha, make_workload
     P, R = 12, 32
-    wl = make_workload("c5", B=P * R, seed=4)
-    wl.n_restarts = R                                   # same generator, fewer restarts per problem
+    wl = make_workload("c5", B=P * 256, seed=4)          # 12 problems ...
+    wl.n_restarts = R                                   # ... same generator, fewer restarts per problem
     tr = Trajectory(wl.args, strict_math=True)
     tr.set_obstacles(wl.obstacles)
     alpha0, start, goal = initial_alpha(wl, tr, 4)
@@ -581,3 +581,88 @@ def test_two_streams_on_one_handle(cuda_ready):
         for i in range(2):
             assert (ins[i][4][:, M.I_STATUS] == M.ST_DONE).all()
             assert torch.equal(ins[i][0], ref[i][0]) and torch.equal(ins[i][4], ref[i][2])
+
+
+@pytest.mark.parametrize("mode,strict", [("bls", True), ("gd", True), ("bls", False)])
+def test_live_obstacle_updates_replay_bit_exact(cuda_ready, mode, strict):
+    """Config 4 without relaunches (fgd_optimize_live): ONE persistent launch while the host publishes new obstacle sets
+    (count changes too) with fgd_set_obstacles_async on a side stream; every team polls the generation counter every 4
+    inner iterations of its trajectory.  Which generation a trajectory saw at which iteration depends on timing, so the
+    kernel records it (switch log) and the oracle REPLAYS that schedule per trajectory through its budgeted entry - the
+    plain loop's semantics (optimizer_BLS.py:79,82,90): bit-identical alpha, counters and loss state (strict mode).
+    Fast mode: the same replay through the budgeted CUDA entry points (relaunch path) gives identical bits."""
+    import torch
+    from irm_motion_planning_b200 import backend
+    from irm_motion_planning_b200.batch import BatchedFGD
+    from irm_motion_planning_b200.workloads import obstacle_swap
+    B, POLL = 600, 4
+    over = {} if mode == "bls" else {"max_outer_iteration": 3}
+    args, tr, obs, start, goal, alpha0 = _setup(B=B, n_obs=256, seed=17, strict=strict, **over)
+    sets = [np.asarray(obs, np.float32)] + [obstacle_swap(k, seed=17) for k in range(1, 40)]
+    eng = BatchedFGD(tr, mode)
+    a = torch.as_tensor(alpha0, device="cuda").clone()
+    s, g = torch.as_tensor(start, device="cuda").contiguous(), torch.as_tensor(goal, device="cuda").contiguous()
+    fs, is_ = eng.new_state(B)
+    log = torch.zeros(B, backend.FGD_SWITCH_LOG, 2, dtype=torch.int32, device="cuda")
+    gen0 = tr.handle.obstacle_generation                 # generation of `obs` (published by _setup)
+    h_before = tr.handle
+    n_pub = eng.optimize_live(a, s, g, fs, is_, sets, poll_every=POLL, period_us=60.0, switch_log=log)
+    torch.cuda.synchronize()
+    assert tr.handle is h_before and tr.handle.obstacle_generation == gen0 + n_pub
+    is_g, a_g, log = is_.cpu().numpy(), a.cpu().numpy(), log.cpu().numpy()
+    assert (is_g[:, M.I_STATUS] == M.ST_DONE).all()
+    n_sw = log[:, 0, 0]
+    assert (n_sw >= 1).all() and n_sw.max() < backend.FGD_SWITCH_LOG
+    assert n_pub >= 3 and (n_sw > 1).mean() > 0.2, (n_pub, n_sw.mean())      # the sets really changed under running trajectories
+    set_of = lambda gen: sets[0] if gen <= gen0 else sets[(gen - gen0) % len(sets)]
+    m = _mirror(args, tr, obs, mode)
+    picks = np.random.default_rng(0).choice(B, 160, replace=False) if strict else np.arange(0)
+    for b in picks:
+        sched = log[b, 1:1 + n_sw[b]]
+        assert sched[0, 0] == 0 and (np.diff(sched[:, 0]) > 0).all() and (sched[1:, 0] % POLL == 0).all()
+        ca, cfs, cis = alpha0[b:b + 1].copy(), *m.new_state(1)
+        for k, (it, gen) in enumerate(sched):
+            m.set_obstacles(set_of(gen))
+            budget = int(sched[k + 1, 0] - it) if k + 1 < len(sched) else -1
+            ca, cfs, cis = m.optimize(ca, start[b:b + 1], goal[b:b + 1], cfs, cis, budget=budget)
+        assert np.array_equal(cis[0], is_g[b]), (b, sched.tolist(), cis[0], is_g[b])
+        assert np.array_equal(ca[0], a_g[b])
+    if not strict:      # fast mode: replay through the relaunch path of the same library
+        tr2 = type(tr)(args, strict_math=False)
+        for b in np.random.default_rng(1).choice(B, 24, replace=False):
+            sched = log[b, 1:1 + n_sw[b]]
+            a2, st2 = alpha0[b:b + 1], None
+            for k, (it, gen) in enumerate(sched):
+                tr2.handle.set_obstacles(set_of(gen))
+                budget = int(sched[k + 1, 0] - it) if k + 1 < len(sched) else -1
+                a2, f2, i2 = _gpu_optimize(tr2, mode, a2, start[b:b + 1], goal[b:b + 1], budget=budget, state=st2)
+                st2 = (f2, i2)
+            assert np.array_equal(i2.cpu().numpy()[0], is_g[b]) and np.array_equal(a2.cpu().numpy()[0], a_g[b])
+    # and a launch without updates equals the plain launch
+    tr.set_obstacles(obs)
+    a1, fs1, is1 = _gpu_optimize(tr, mode, alpha0[:64], start[:64], goal[:64])
+    a3 = torch.as_tensor(alpha0[:64], device="cuda").clone()
+    fs3, is3 = eng.new_state(64)
+    tr.handle.optimize_live(mode, 64, a3, s[:64].contiguous(), g[:64].contiguous(), fs3, is3, POLL)
+    torch.cuda.synchronize()
+    assert torch.equal(a1, a3) and torch.equal(is1, is3)
+
+
+def test_live_rejects_multi_warp_teams_and_oversized_capacity(cuda_ready):
+    import torch
+    from irm_motion_planning_b200 import backend
+    from irm_motion_planning_b200.batch import BatchedFGD
+    args, tr, obs, start, goal, alpha0 = _setup(T=100, n_obs=20, B=4, seed=1)
+    eng = BatchedFGD(tr, "bls")
+    fs, is_ = eng.new_state(4)
+    with pytest.raises(backend.FgdError) as ei:
+        tr.handle.optimize_live("bls", 4, torch.as_tensor(alpha0, device="cuda"), torch.as_tensor(start, device="cuda"),
+                                torch.as_tensor(goal, device="cuda"), fs, is_, 8)
+    assert ei.value.status == 2
+    args, tr, obs, start, goal, alpha0 = _setup(T=50, n_obs=20, B=4, seed=1, capacity=8192)
+    eng = BatchedFGD(tr, "bls")
+    fs, is_ = eng.new_state(4)
+    with pytest.raises(backend.FgdError) as ei:
+        tr.handle.optimize_live("bls", 4, torch.as_tensor(alpha0, device="cuda"), torch.as_tensor(start, device="cuda"),
+                                torch.as_tensor(goal, device="cuda"), fs, is_, 8)
+    assert ei.value.status == 4

@@ -219,6 +219,11 @@ int fgd_launch_geometry(const FgdHandle *h, int32_t B, int32_t *grid, int32_t *b
                         int32_t *warps_per_trajectory);
 int64_t fgd_kernel_launches(const FgdHandle *h);   /* kernels launched through this handle so far */
 int64_t fgd_zero_copy_calls(const FgdHandle *h);   /* fgd_optimize_host_io calls served without staging copies */
+/* BLS launches that ran the speculative line search: for batches of at most 2 x SM-count trajectories (T <= 64, end-effector
+ * cost) fgd_optimize_bls gives every trajectory a CTA of four warps that evaluate four consecutive Armijo candidates at
+ * once and select the first accepting one in the reference's order (optimizer_BLS.py:131-150) - same iterates, bit for
+ * bit, in fewer sequential trips.  Environment FGD_SPEC_MAX_BATCH=0 disables it (A/B measurements). */
+int64_t fgd_speculative_launches(const FgdHandle *h);
 /* FP32 FFMA throughput of the current device (TFLOP/s, best of 5 launches of a
  * pure-FFMA kernel): the measured denominator of the harness's roofline.frac. */
 int fgd_measure_fp32_peak(FgdHandle *h, double *tflops_out, void *stream);

@@ -51,7 +51,7 @@ EXPORTED_SYMBOLS = (
     "fgd_create", "fgd_destroy", "fgd_status_string", "fgd_last_cuda_error", "fgd_set_obstacles_async",
     "fgd_obstacle_count", "fgd_obstacle_generation", "fgd_optimize_live", "fgd_eval_cost_grad", "fgd_optimize_bls", "fgd_optimize_gd", "fgd_optimize_host",
     "fgd_argmin_per_problem", "fgd_launch_geometry", "fgd_kernel_launches", "fgd_abi_version",
-    "fgd_measure_fp32_peak", "fgd_measure_mufu_peak", "fgd_set_init_basis", "fgd_init_trajectory", "fgd_optimize_host_io", "fgd_zero_copy_calls",
+    "fgd_measure_fp32_peak", "fgd_measure_mufu_peak", "fgd_set_init_basis", "fgd_init_trajectory", "fgd_optimize_host_io", "fgd_zero_copy_calls", "fgd_speculative_launches",
 )
 
 _lib = None
@@ -92,6 +92,8 @@ def load_library(path: Optional[str] = None):
     lib.fgd_kernel_launches.restype = C.c_int64
     lib.fgd_zero_copy_calls.argtypes = [vp]
     lib.fgd_zero_copy_calls.restype = C.c_int64
+    lib.fgd_speculative_launches.argtypes = [vp]
+    lib.fgd_speculative_launches.restype = C.c_int64
     lib.fgd_measure_fp32_peak.argtypes = [vp, C.POINTER(C.c_double), vp]
     lib.fgd_measure_mufu_peak.argtypes = [vp, C.POINTER(C.c_double), vp]
     if lib.fgd_abi_version() != FGD_ABI_VERSION:
@@ -288,6 +290,10 @@ class Handle:
 
     def kernel_launches(self) -> int:
         return int(self._lib.fgd_kernel_launches(self._h))
+
+    def speculative_launches(self) -> int:
+        """BLS launches that ran the speculative (parallel-candidate) line search kernel."""
+        return int(self._lib.fgd_speculative_launches(self._h))
 
     def zero_copy_calls(self) -> int:
         """optimize_host_io calls that ran zero-copy on page-locked buffers (no staging copies)."""

@@ -31,6 +31,8 @@ struct FgdHandle {
     int *h_dbg = nullptr, *d_dbg = nullptr;   // FGD_DEBUG_MARK builds: host-mapped progress markers
     cudaEvent_t obs_event = nullptr, launch_event = nullptr;
     bool obs_event_pending = false, launch_event_pending = false;
+    int spec_max_batch = 0;    // BLS batches up to this size run the speculative line-search kernel (one trajectory per CTA)
+    long long spec_launches = 0;
     int last_cuda_error = 0;
     long long launches = 0, zero_copy_calls = 0, opt_launches = 0;
     // scratch for the host-buffer entry point
@@ -91,6 +93,29 @@ cudaError_t launch_eval(const DevParams &p, const EvalPtrs &e, int grid, size_t 
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     kern<<<grid, NW * 32, smem, st>>>(p, e);
+    return cudaGetLastError();
+}
+
+// Speculative line search (latency mode, fgd_kernels.cuh): SPEC_WARPS replicas of one trajectory per CTA, tables in TMEM.
+constexpr int SPEC_WARPS = 4;
+template <bool STRICT, int TC>
+cudaError_t launch_spec(const DevParams &p, int grid, size_t smem, cudaStream_t st)
+{
+    auto kern = fgd_optimize_kernel<1, STRICT, K_TMEM, SPEC_WARPS, 2, false, TC, 0, SPEC_WARPS>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, SPEC_WARPS * 32, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+// Live obstacle updates (fgd_optimize_live): the default T <= 64 kernel layout with a private obstacle set per team.
+template <bool STRICT, int TC>
+cudaError_t launch_live(const DevParams &p, int grid, size_t smem, cudaStream_t st)
+{
+    auto kern = p.mode == 0 ? fgd_optimize_kernel<1, STRICT, K_TMEM, 16, 1, false, TC, 0, 0, true> : fgd_optimize_kernel<1, STRICT, K_TMEM, 16, 1, false, TC, 1, 0, true>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, 16 * 32, smem, st>>>(p);
     return cudaGetLastError();
 }
 
@@ -198,15 +223,17 @@ cudaError_t dispatch_eval(int WPT, bool strict, bool arm, const DevParams &p, co
     return cudaErrorInvalidValue;
 }
 
-Geometry geometry(const FgdHandle *h, int B, int n_obs, bool live = false)
+Geometry geometry(const FgdHandle *h, int B, int n_obs)
 {
     Geometry g;
     const int nw = warps_per_cta(h->variant, h->WPT);
     const int teams = nw / h->WPT;
     g.block = nw * 32;
-    g.smem = (int)make_layout(h->T, h->TP, live ? h->cfg.obstacle_capacity : n_obs, k_source(h->variant, h->WPT), teams, h->WPT, live).bytes();
+    g.smem = (int)make_layout(h->T, h->TP, n_obs, k_source(h->variant, h->WPT), teams, h->WPT).bytes();
     const int occ = dispatch_occ(h->variant, h->WPT, h->T, h->cfg.strict_math != 0, h->cfg.whole_arm_cost != 0, (size_t)g.smem);
-    const long long need = ((long long)B + teams - 1) / teams;
+    // one CTA per trajectory until every SM has its share: a batch smaller than the machine spreads over all SMs (the
+    // first pick of every team is static, fetch_slot), larger batches run occupancy x SMs persistent CTAs
+    const long long need = (long long)B;
     const long long cap = (long long)occ * h->num_sms;
     g.grid = (int)(need < cap ? need : cap);
     if (g.grid < 1) g.grid = 1;
@@ -252,12 +279,32 @@ int run_optimize(FgdHandle *h, int mode, int B, float *d_alpha, const float *d_s
     const bool live = poll_every > 0;
     if (live) {
         if (h->WPT != 1) return FGD_ERR_UNSUPPORTED_T;
+        if (h->cfg.whole_arm_cost) return FGD_ERR_INVALID_ARGUMENT;
         p.poll_every = poll_every; p.switch_log = d_switch_log;
     }
-    const Geometry g = geometry(h, B, p.n_obs, live);
+    Geometry g = geometry(h, B, p.n_obs);
+    if (live) {         // always the tensor-memory layout: 16 single-warp teams per CTA, one CTA per SM
+        g.block = 16 * 32;
+        g.smem = (int)make_layout(h->T, h->TP, h->cfg.obstacle_capacity, K_TMEM, 16, 1, true).bytes();
+        g.grid = B < h->num_sms ? B : h->num_sms;
+    }
     if (g.smem + 64 > h->max_smem_optin) return FGD_ERR_TOO_MANY_OBSTACLES;
     CK(cudaMemsetAsync(p.queue, 0, sizeof(unsigned), st));      // this launch's own counter (launches on other streams keep theirs)
-    CK(dispatch_opt(h->variant, h->WPT, h->cfg.strict_math != 0, h->cfg.whole_arm_cost != 0, p, g.grid, (size_t)g.smem, st));
+    const bool spec = mode == 0 && h->WPT == 1 && h->variant == 0 && !h->cfg.whole_arm_cost && !live && B <= h->spec_max_batch;
+    if (spec) {
+        g.block = SPEC_WARPS * 32;
+        g.smem = (int)make_layout(h->T, h->TP, p.n_obs, K_TMEM, SPEC_WARPS, 1).bytes();
+        g.grid = B < 2 * h->num_sms ? B : 2 * h->num_sms;
+        const bool strict = h->cfg.strict_math != 0;
+        CK(use_tc(p.T) ? (strict ? launch_spec<true, FGD_TC>(p, g.grid, (size_t)g.smem, st) : launch_spec<false, FGD_TC>(p, g.grid, (size_t)g.smem, st))
+                       : (strict ? launch_spec<true, 0>(p, g.grid, (size_t)g.smem, st) : launch_spec<false, 0>(p, g.grid, (size_t)g.smem, st)));
+        h->spec_launches += 1;
+    } else if (live) {
+        const bool strict = h->cfg.strict_math != 0;
+        CK(use_tc(p.T) ? (strict ? launch_live<true, FGD_TC>(p, g.grid, (size_t)g.smem, st) : launch_live<false, FGD_TC>(p, g.grid, (size_t)g.smem, st))
+                       : (strict ? launch_live<true, 0>(p, g.grid, (size_t)g.smem, st) : launch_live<false, 0>(p, g.grid, (size_t)g.smem, st)));
+    } else
+        CK(dispatch_opt(h->variant, h->WPT, h->cfg.strict_math != 0, h->cfg.whole_arm_cost != 0, p, g.grid, (size_t)g.smem, st));
     h->launches += 1;
     h->opt_launches += 1;
     if (!live) {        // a live kernel copies what it needs and validates it against the slot header; it must not hold up the publisher
@@ -387,6 +434,8 @@ int fgd_create(const FgdConfig *cfg, FgdHandle **out)
     CKC(cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
     // K and dK go to shared memory when both fit beside the operand buffers of at least one slot per warp
     if (const char *e = std::getenv("FGD_VARIANT")) { const int v = std::atoi(e); if (variant_exists(v, h->WPT)) h->variant = v; }
+    h->spec_max_batch = 2 * h->num_sms;          // up to two 4-warp CTAs per SM: beyond that the warps are better used on more trajectories
+    if (const char *e = std::getenv("FGD_SPEC_MAX_BATCH")) h->spec_max_batch = std::atoi(e);      // 0 disables (A/B measurements)
     {   // the whole obstacle set is staged in shared memory next to the operand buffers (and, for the kernels that keep
         // them there, the K tables): the capacity must fit both the optimiser and the evaluation kernel
         const int nw = warps_per_cta(h->variant, h->WPT), nwe = eval_warps_per_cta(h->WPT);
@@ -690,6 +739,7 @@ int fgd_launch_geometry(const FgdHandle *h, int32_t B, int32_t *grid, int32_t *b
 
 int64_t fgd_kernel_launches(const FgdHandle *h) { return h ? h->launches : 0; }
 int64_t fgd_zero_copy_calls(const FgdHandle *h) { return h ? h->zero_copy_calls : 0; }
+int64_t fgd_speculative_launches(const FgdHandle *h) { return h ? h->spec_launches : 0; }
 
 #if defined(FGD_DEBUG_MARK) || defined(FGD_PHASE_CLOCKS)
 int *fgd_debug_buffer(FgdHandle *h) { return h->h_dbg; }

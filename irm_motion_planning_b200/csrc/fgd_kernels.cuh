@@ -98,19 +98,40 @@ __device__ __forceinline__ void save_slot(const DevParams &p, const Team<WPT> &G
     G.sync();                                         // stage is free again
 }
 
-// Pull the next unfinished trajectory from the batch queue (team-uniform).
-template <int WPT, int MODE>
-__device__ __forceinline__ void fetch_slot(const DevParams &p, const Team<WPT> &G, Slot &st, int &kind, f2 (&a)[3], float *stage)
+// Speculative line search (SPEC replicas of one trajectory per CTA): what the replicas exchange per candidate round.
+struct SpecScratch {
+    float loss[8], toc[8];
+    int ful[8], flag[8];       // flag: 0 = this candidate passes the Armijo test, 1 = rejected, 2 = beyond max_bls_iteration
+    unsigned nz[R];            // non-zero rows of the winner's velocity-gradient operand
+    unsigned fetch;            // queue index of the trajectory all replicas pick up
+};
+
+// Pull the next unfinished trajectory (team-uniform).  The first pick of every team is static - team t of CTA c takes
+// trajectory t * gridDim + c - so that a batch smaller than the resident teams spreads over all SMs instead of filling the
+// first CTAs; later picks come from the global queue counter, which starts behind the static round.
+// SPEC: all warps of the CTA are replicas of ONE team; warp 0 picks, everybody loads.
+template <int WPT, int MODE, int TEAMS, bool SP>
+__device__ __forceinline__ void fetch_slot(const DevParams &p, const Team<WPT> &G, Slot &st, int &kind, f2 (&a)[3], float *stage, bool &first,
+                                           SpecScratch *sp)
 {
+    constexpr int TEAMS_Q = SP ? 1 : TEAMS;
     for (;;) {
         unsigned idx = 0;
-        if constexpr (WPT == 1) {
-            if (G.lane == 0) idx = atomicAdd(p.queue, 1u);
+        if (first) {
+            first = false;
+            idx = (SP ? 0u : (unsigned)((threadIdx.x >> 5) / WPT)) * gridDim.x + blockIdx.x;
+        } else if constexpr (SP) {
+            __syncthreads();                          // the previous round's readers are done
+            if (threadIdx.x == 0) sp->fetch = (unsigned)TEAMS_Q * gridDim.x + atomicAdd(p.queue, 1u);
+            __syncthreads();
+            idx = sp->fetch;
+        } else if constexpr (WPT == 1) {
+            if (G.lane == 0) idx = (unsigned)TEAMS_Q * gridDim.x + atomicAdd(p.queue, 1u);
             idx = __shfl_sync(FULL, idx, 0);
         } else {
             unsigned *xf = reinterpret_cast<unsigned *>(G.xch + XCH_FETCH);
             G.sync();                                 // the previous round's readers are done
-            if (G.tl == 0) *xf = atomicAdd(p.queue, 1u);
+            if (G.tl == 0) *xf = (unsigned)TEAMS_Q * gridDim.x + atomicAdd(p.queue, 1u);
             G.sync();
             idx = *xf;
         }
@@ -255,7 +276,7 @@ __device__ __forceinline__ float2 ld_volatile_f2(const float2 *p)
 __device__ __forceinline__ bool live_refresh(const DevParams &p, const int lane, float2 *sObsT, int &cur_gen, int &n_obs)
 {
     bool changed = false;
-    for (;;) {
+    for (int tries = 0; tries < 65536; ++tries) {             // bounded: a publisher that died mid-update must not hang the kernel
         int gen = 0, hdr = 0, cnt = 0;
         if (lane == 0) gen = ld_acquire_sys(p.obs_meta);
         gen = __shfl_sync(FULL, gen, 0);
@@ -275,6 +296,8 @@ __device__ __forceinline__ bool live_refresh(const DevParams &p, const int lane,
         cur_gen = gen; n_obs = cnt; changed = true;
         return true;
     }
+    if (cur_gen < 0) n_obs = 0;                                // never got a consistent set: run without obstacles rather than on garbage
+    return changed;
 }
 
 // switch log of trajectory b: entry 0 = (count, 0), entries 1..count = (inner iterations completed, generation adopted)
@@ -298,16 +321,27 @@ __device__ __forceinline__ void log_switch(const DevParams &p, const int lane, c
 // TC > 0: instance specialised for T == TC (the reference's default T = 50): the contraction loops are fully unrolled.
 // MODE: 0 = backtracking line search (optimizer_BLS.py), 1 = gradient descent (optimizer_GD.py) - a compile-time
 // constant so that each instance carries only its own state machine.
-template <int WPT, bool STRICT, int KS, int NW, int MINB, bool ARM, int TC, int MODE>
+// SPEC > 0 (BLS, single-warp teams, NW == SPEC): latency mode for batches smaller than the machine.  The CTA runs ONE
+// trajectory; its SPEC warps are replicas that hold the same state and evaluate the Armijo candidates j, j+1, ..., j+SPEC-1
+// of a line search AT THE SAME TIME (north_star item 5; the reference tries them one after the other,
+// optimizer_BLS.py:131-150).  The first accepting candidate in the reference's order wins; counters, hash and step size
+// are advanced exactly as the sequential search would have - candidates evaluated beyond the winner leave no trace - so
+// the iterates are the reference's bit for bit.  Gradient trips are computed redundantly by all replicas from the
+// winner's operand buffer.
+// LIVE: live obstacle updates (fgd_optimize_live): a private obstacle set per team, polled and refreshed in the kernel.
+template <int WPT, bool STRICT, int KS, int NW, int MINB, bool ARM, int TC, int MODE, int SPEC = 0, bool LIVE = false>
 __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __grid_constant__ DevParams p)
 {
+    constexpr bool SP = SPEC > 0;
+    static_assert(!LIVE || (WPT == 1 && !SP), "live obstacle updates: single-warp teams");
+    static_assert(!SP || (WPT == 1 && MODE == 0 && NW == SPEC && SPEC <= 8), "speculative line search: BLS, single-warp replicas, one trajectory per CTA");
     static_assert(TC == 0 || KS == K_TMEM, "compile-time T: TMEM instances only");
     static_assert(WPT == 1 || NW == WPT, "multi-warp teams own their CTA");
     static_assert(KS != K_TMEM || (WPT == 1 && NW >= 4 && NW % 4 == 0), "TMEM tables: single-warp teams, whole lane quadrants");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int TEAMS = NW / WPT;
     const int T = TC > 0 ? TC : p.T;
-    const bool live = WPT == 1 && p.poll_every > 0;            // live obstacle updates: a private obstacle set per team
+    constexpr bool live = LIVE;
     const SmemLayout L = make_layout(T, WPT * 32 * R, live ? p.obs_cap : p.n_obs, KS, TEAMS, WPT, live);
     float *sKD = reinterpret_cast<float *>(smem_raw);
     float *sKO = sKD + 2 * L.k_floats;
@@ -324,8 +358,16 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
     unsigned tk = 0;
     if constexpr (KS == K_TMEM) tk = tmem_stage_tables(p);
     (void)kd; (void)ko; (void)tk;
-    int n_obs = p.n_obs, cur_gen = -1, polled_at = -1, n_switch = 0;      // live: the team's obstacle set and poll bookkeeping
-    (void)cur_gen; (void)polled_at; (void)n_switch;
+    int n_obs_live = 0, cur_gen = -1, polled_at = -1, n_switch = 0;       // LIVE: the team's obstacle set and poll bookkeeping
+    (void)n_obs_live; (void)cur_gen; (void)polled_at; (void)n_switch;
+    __shared__ SpecScratch sp_mem;                                          // SPEC only (a few words)
+    SpecScratch *sp = &sp_mem;
+    const int rep = SP ? (int)(threadIdx.x >> 5) : 0;                       // replica index = candidate offset in a round
+    int win = rep;                                                          // replica whose operand buffers feed the next gradient trip
+    float lr_mine = 0.0f;                                                   // step size of this replica's candidate
+    auto gsync = [&]() { if constexpr (SP) __syncthreads(); else G.sync(); };
+    bool first_fetch = true;
+    (void)win; (void)lr_mine;
 
     int kind = K_IDLE;
     Slot st;                   // team-uniform loop state of this team's trajectory (registers)
@@ -346,15 +388,19 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
         (void)was_back;
         if (!boot) {
             if (kind == K_IDLE) break;
-            G.sync();                                                                    // operands complete
+            gsync();                                                                     // operands complete
             if constexpr (KS == K_TMEM) {
                 if (kind != K_BACK) contract_tm<true, TC>(tk, T, XA, XA, y1, y2);                // forward: K x, dK x
-                else contract_back_tm<TC>(tk, T, XA, XB, nz, y1, y2);                            // backward: K G_q + dK (-G_v)
+                else if constexpr (SP) {                                                         // the winner's gradient operands
+                    const float4 *XAw = reinterpret_cast<const float4 *>(sTeams + (size_t)win * L.team_bytes());
+                    if (win != rep) { nz[0][0] = sp->nz[0]; nz[0][1] = sp->nz[1]; }
+                    contract_back_tm<TC>(tk, T, XAw, XAw + L.x_rows, nz, y1, y2);
+                } else contract_back_tm<TC>(tk, T, XA, XB, nz, y1, y2);                          // backward: K G_q + dK (-G_v)
             } else {
                 if (kind != K_BACK) contract<WPT, KS, true>(kd, T, XA, XA, y1, y2);
                 else { load_nz<WPT>(G, nz); contract_back<WPT, KS>(ko, kd, T, XA, XB, nz, y1, y2); }
             }
-            G.sync();                                                                    // operands consumed
+            gsync();                                                                     // operands consumed
         }
         PCLK(was_back ? 4 : 0);
         TRACE("lane %d trip boot=%d kind=%d\n", threadIdx.x, (int)boot, kind);
@@ -393,12 +439,53 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
             Rows<ARM> Rw;
             float loss_c, toc_c;
             int ful_c;
-            cost_phase<WPT, STRICT, ARM>(p, T, sObs, n_obs, G, y1, y2, st.start, st.goal, st.lam_sg, st.lam_jl, Rw, loss_c, toc_c, ful_c);
+            cost_phase<WPT, STRICT, ARM>(p, T, sObs, LIVE ? n_obs_live : p.n_obs, G, y1, y2, st.start, st.goal, st.lam_sg, st.lam_jl, Rw, loss_c, toc_c, ful_c);
             PCLK(1);
             bool accept = false;
             if (kind == K_EVAL0) {
                 st.loss = loss_c; st.toc = toc_c; st.ful = ful_c;
                 accept = true; want_head = true;
+                win = rep;
+            } else if constexpr (SP) {
+                // ---- one round of the speculative line search: replica r holds candidate j + r ----
+                const float loss = st.loss;
+                const float req = loss - (p.bls_alpha * lr_mine) * st.alpha_norm;        // Armijo test, optimizer_BLS.py:141-149
+                const int flag = (st.j + rep >= p.max_bls) ? 2 : ((loss_c > req) ? 1 : 0);
+                if (G.lane == 0) { sp->loss[rep] = loss_c; sp->toc[rep] = toc_c; sp->ful[rep] = ful_c; sp->flag[rep] = flag; }
+                __syncthreads();
+                int acc = -1, n_rej = 0;
+                bool stop = false;
+#pragma unroll
+                for (int r = 0; r < SPEC; ++r) {
+                    const int f = sp->flag[r];
+                    if (!stop) { if (f == 1) n_rej += 1; else { stop = true; if (f == 0) acc = r; } }
+                }
+                for (int i = 0; i < n_rej; ++i) {          // the rejected candidates the sequential search went through
+                    st.lr = st.lr * p.bls_bm; hash_step(st, 1u);
+                    st.j += 1; st.cand_evals += 1;
+                }
+                if (acc >= 0) {
+                    st.cand_evals += 1;
+                    const float lr = st.lr, lc = sp->loss[acc];
+                    const bool minimized = (loss - lc < p.eps_loop);                   // optimizer_BLS.py:178
+                    f2 c[3];
+                    make_candidate(p, lr, a, d, c);             // the winner's candidate, recomputed by every replica: same bits
+#pragma unroll
+                    for (int b = 0; b < 3; ++b) a[b] = c[b];
+                    st.lr = lr * p.bls_bp;
+                    st.accepts += 1; hash_step(st, 2u);
+                    st.ful = sp->ful[acc]; st.toc = sp->toc[acc]; st.last_new = lc; st.loss = lc;
+                    if (minimized) { hash_step(st, 3u); want_end = true; }
+                    else { st.inner += 1; want_head = true; }
+                    win = acc;
+                    accept = (rep == acc);                      // only the winner holds the rows of the accepted candidate
+                } else if (st.j < p.max_bls) {
+                    want_cand = true;
+                } else {
+                    st.last_new = loss;                         // every candidate rejected: new_loss := loss (optimizer_BLS.py:170,178)
+                    if (loss - loss < p.eps_loop) { hash_step(st, 3u); want_end = true; }
+                    else { st.inner += 1; want_eval = true; }
+                }
             } else {
                 st.cand_evals += 1;
                 const float lr = st.lr, loss = st.loss;
@@ -437,6 +524,9 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
                 }
             }
             if (accept) grad_phase<WPT, ARM>(p, T, G, Rw, st.start, st.goal, st.lam_sg, st.lam_jl, XA, XB, nz);
+            if constexpr (SP) {
+                if (accept && kind == K_CAND && G.lane == 0) { sp->nz[0] = nz[0][0]; sp->nz[1] = nz[0][1]; }
+            }
         }
         PCLK(was_back ? 5 : 2);
         // ---- common tail: loop heads, retirement, refill -------------------------------------
@@ -444,12 +534,12 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
         if (want_head) {                                         // optimizer_BLS.py:155-157
             if (st.inner < p.max_inner) {
                 bool switched = false;
-                if constexpr (WPT == 1) {
+                if constexpr (LIVE) {
                     // live obstacle updates: every poll_every inner iterations of this trajectory look for a newer obstacle set
                     // (plain-loop semantics, optimizer_BLS.py:79,82,90: the environment is re-read between iterations)
-                    if (live && st.inner_total != polled_at && st.inner_total % p.poll_every == 0) {
+                    if (st.inner_total != polled_at && st.inner_total % p.poll_every == 0) {
                         polled_at = st.inner_total;
-                        switched = live_refresh(p, G.lane, sObs, cur_gen, n_obs);
+                        switched = live_refresh(p, G.lane, sObs, cur_gen, n_obs_live);
                         if (switched) log_switch(p, G.lane, st.traj, n_switch, st.inner_total, cur_gen);
                     }
                 }
@@ -476,12 +566,12 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
             }
         }
         if (retire || save_active || boot) {
-            if (!boot) save_slot<WPT>(p, G, st, retire ? FGD_ST_DONE : FGD_ST_ACTIVE, a, reinterpret_cast<float *>(XA));
-            fetch_slot<WPT, MODE>(p, G, st, kind, a, reinterpret_cast<float *>(XA));
+            if (!boot && rep == 0) save_slot<WPT>(p, G, st, retire ? FGD_ST_DONE : FGD_ST_ACTIVE, a, reinterpret_cast<float *>(XA));
+            fetch_slot<WPT, MODE, TEAMS, SP>(p, G, st, kind, a, reinterpret_cast<float *>(XA), first_fetch, sp);
             want_eval = (kind != K_IDLE);
-            if constexpr (WPT == 1) {
-                if (live && kind != K_IDLE) {                  // a trajectory starts with the latest obstacle set
-                    live_refresh(p, G.lane, sObs, cur_gen, n_obs);
+            if constexpr (LIVE) {
+                if (kind != K_IDLE) {                          // a trajectory starts with the latest obstacle set
+                    live_refresh(p, G.lane, sObs, cur_gen, n_obs_live);
                     n_switch = 0; polled_at = st.inner_total;
                     log_switch(p, G.lane, st.traj, n_switch, st.inner_total, cur_gen);
                 }
@@ -495,7 +585,11 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
         }
         if (want_cand) {
             f2 c[3];
-            make_candidate(p, st.lr, a, d, c);
+            lr_mine = st.lr;
+            if constexpr (SP) {
+                for (int i = 0; i < rep; ++i) lr_mine = lr_mine * p.bls_bm;      // the step the sequential search would try rep rejections later
+            }
+            make_candidate(p, lr_mine, a, d, c);
             write_rows<WPT>(T, G, c, XA);
         }
         boot = false;

@@ -606,7 +606,7 @@ def test_live_obstacle_updates_replay_bit_exact(cuda_ready, mode, strict):
     log = torch.zeros(B, backend.FGD_SWITCH_LOG, 2, dtype=torch.int32, device="cuda")
     gen0 = tr.handle.obstacle_generation                 # generation of `obs` (published by _setup)
     h_before = tr.handle
-    n_pub = eng.optimize_live(a, s, g, fs, is_, sets, poll_every=POLL, period_us=60.0, switch_log=log)
+    n_pub = eng.optimize_live(a, s, g, fs, is_, sets, poll_every=POLL, period_us=100.0, switch_log=log, max_sets=45)
     torch.cuda.synchronize()
     assert tr.handle is h_before and tr.handle.obstacle_generation == gen0 + n_pub
     is_g, a_g, log = is_.cpu().numpy(), a.cpu().numpy(), log.cpu().numpy()
@@ -666,3 +666,41 @@ def test_live_rejects_multi_warp_teams_and_oversized_capacity(cuda_ready):
         tr.handle.optimize_live("bls", 4, torch.as_tensor(alpha0, device="cuda"), torch.as_tensor(start, device="cuda"),
                                 torch.as_tensor(goal, device="cuda"), fs, is_, 8)
     assert ei.value.status == 4
+
+
+@pytest.mark.parametrize("T,B,over", [(50, 150, {}), (50, 296, {"max_bls_iteration": 6}), (33, 40, {"bls_alpha": 1e3, "max_outer_iteration": 2}),
+                                      (64, 7, {"max_bls_iteration": 3, "bls_beta_minus": 0.7}), (50, 1, {})])
+def test_speculative_line_search_equals_sequential(cuda_ready, monkeypatch, T, B, over):
+    """north_star item 5: for batches smaller than the machine the Armijo candidates of a line search are evaluated IN
+    PARALLEL (four warps per trajectory, four consecutive candidates per round) and the first accepting one in the
+    reference's order is selected (optimizer_BLS.py:131-150).  The iterates, step sizes, counters and decision hash equal
+    the sequential kernel's bit for bit - in fast mode too (same arithmetic) - and the oracle's in strict mode; candidate
+    counts that are not a multiple of four and line searches that reject every candidate included."""
+    from irm_motion_planning_b200.trajectory import Trajectory
+    for strict in (True, False):
+        args, tr, obs, start, goal, alpha0 = _setup(T=T, B=B, seed=B + 1, strict=strict, **over)
+        s0 = tr.handle.speculative_launches()
+        a, fs, is_ = _gpu_optimize(tr, "bls", alpha0, start, goal)
+        assert tr.handle.speculative_launches() == s0 + 1
+        monkeypatch.setenv("FGD_SPEC_MAX_BATCH", "0")
+        tr_seq = Trajectory(args, strict_math=strict)
+        monkeypatch.delenv("FGD_SPEC_MAX_BATCH")
+        tr_seq.set_obstacles(obs)
+        a2, fs2, is2 = _gpu_optimize(tr_seq, "bls", alpha0, start, goal)
+        assert tr_seq.handle.speculative_launches() == 0
+        import torch
+        assert torch.equal(is_, is2) and torch.equal(a, a2) and torch.equal(fs[:, :6], fs2[:, :6])
+        if strict:
+            ca, cfs, cis = _mirror(args, tr, obs, "bls").optimize(alpha0, start, goal)
+            assert np.array_equal(is_.cpu().numpy(), cis) and np.array_equal(a.cpu().numpy(), ca)
+            if "bls_alpha" in over:
+                assert (cis[:, M.I_ACCEPTS] == 0).all() and (cis[:, M.I_CAND_EVALS] >= 20).all()     # every candidate rejected
+    # budgeted launches resume identically under speculation
+    args, tr, obs, start, goal, alpha0 = _setup(T=50, B=20, seed=3)
+    ca, cfs, cis = _mirror(args, tr, obs, "bls").optimize(alpha0, start, goal)
+    a, fs, is_ = _gpu_optimize(tr, "bls", alpha0, start, goal, budget=5)
+    for _ in range(1000):
+        if (is_.cpu().numpy()[:, M.I_STATUS] == M.ST_DONE).all():
+            break
+        a, fs, is_ = _gpu_optimize(tr, "bls", a, start, goal, budget=5, state=(fs, is_))
+    assert np.array_equal(a.cpu().numpy(), ca) and np.array_equal(is_.cpu().numpy(), cis)

@@ -599,7 +599,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
 #endif
     }
 #ifdef FGD_PHASE_CLOCKS
-    if (p.dbg && blockIdx.x == 0 && G.tl == 0 && pc[7] > 2)
+    if (p.dbg && blockIdx.x == 0 && (SP ? threadIdx.x == 0 : G.tl == 0) && pc[7] > 2)
         for (int i = 0; i < 8; ++i) p.dbg[i] = (int)(pc[i] >> 4);      // units of 16 cycles
 #endif
     if constexpr (KS == K_TMEM) tmem_release_tables(tk);

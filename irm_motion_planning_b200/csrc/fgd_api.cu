@@ -16,7 +16,7 @@ struct FgdHandle {
     DevParams base;            // everything except the per-call batch pointers
     int T, TP, WPT, variant = 0;
     int device, num_sms, max_smem_optin;
-    float *d_KD = nullptr, *d_KO = nullptr;
+    float *d_KD = nullptr, *d_KO = nullptr, *d_DO = nullptr;
     float *d_init = nullptr;   // [2T + 9]: u = K^-1 1, w = K^-1 c, J^-1 (fgd_set_init_basis)
     // obstacle ring: generation g lives in slot g % FGD_OBS_RING (fgd_set_obstacles_async)
     float *d_obs_ring = nullptr;           // [FGD_OBS_RING][capacity][2]
@@ -55,14 +55,14 @@ struct Geometry { int grid, block, smem; };
 inline int warps_per_trajectory(int T) { return T <= 64 ? 1 : (T <= 128 ? 2 : 4); }
 
 // (variant, WPT, KSRC, NW, MINB): the instantiated optimiser kernels.  WPT warps per trajectory; KSRC: where the K tables
-// live - tensor memory (K_TMEM, T <= 64), shared memory (K_SMEM, T <= 64) or L2 (K_L2); NW warps per CTA (= WPT for
-// multi-warp teams), MINB = min CTAs per SM (register cap).  Variant 0 is the default; variant 1 exists for A/B
-// measurements (env FGD_VARIANT): the shared-memory tables for T <= 64.  The TMEM kernel runs as ONE 16-warp CTA per SM:
-// cudaOccupancyMaxActiveBlocksPerMultiprocessor reported 1 CTA/SM for an 8-warp TMEM instance whose registers and shared
-// memory allow 2 (a forced grid of 2 per SM measured the same throughput as this layout).
+// live - tensor memory (K_TMEM), shared memory (K_SMEM, T <= 64) or L2 (K_L2); NW warps per CTA, MINB = min CTAs per SM
+// (register cap).  Variant 0 is the default: ONE 16-warp CTA per SM with the tables in tensor memory - 16 single-warp teams
+// (T <= 64), 8 two-warp teams (T <= 128, K and dK in TMEM) or 4 four-warp teams (T <= 256, K in TMEM, dK from L2), the
+// multi-warp teams on named barriers.  Variant 1 exists for A/B measurements (env FGD_VARIANT): shared-memory tables for
+// T <= 64, one team per CTA with the tables in L2 for T > 64 (the round-1 layout).
 #define FGD_FOR_CONFIGS(X) \
-    X(0, 1, K_TMEM, 16, 1) X(0, 2, K_L2, 2, 8) X(0, 4, K_L2, 4, 4) \
-    X(1, 1, K_SMEM, 8, 2)
+    X(0, 1, K_TMEM, 16, 1) X(0, 2, K_TMEM, 16, 1) X(0, 4, K_TMEM, 16, 1) \
+    X(1, 1, K_SMEM, 8, 2) X(1, 2, K_L2, 2, 8) X(1, 4, K_L2, 4, 4)
 // (WPT, KSRC, NW): the evaluation kernels (parity hook; tables in shared memory / L2)
 #define FGD_FOR_EVAL_CONFIGS(X) X(1, K_SMEM, 8) X(2, K_L2, 2) X(4, K_L2, 4)
 
@@ -186,7 +186,7 @@ cudaError_t dispatch_opt(int v, int WPT, bool strict, bool arm, const DevParams 
 {
 #define X(V_, W_, KS_, NW_, MB_)                                                                             \
     if (v == V_ && WPT == W_) {                                                                               \
-        if constexpr (KS_ == K_TMEM) {                                                                        \
+        if constexpr (KS_ == K_TMEM && W_ == 1) {                                                             \
             if (use_tc(p.T)) return launch_sa<W_, KS_, NW_, MB_, FGD_TC>(strict, arm, p, grid, smem, st);     \
         }                                                                                                     \
         return launch_sa<W_, KS_, NW_, MB_, 0>(strict, arm, p, grid, smem, st);                               \
@@ -200,7 +200,7 @@ int dispatch_occ(int v, int WPT, int T, bool strict, bool arm, size_t smem)
 {
 #define X(V_, W_, KS_, NW_, MB_)                                                                             \
     if (v == V_ && WPT == W_) {                                                                               \
-        if constexpr (KS_ == K_TMEM) {                                                                        \
+        if constexpr (KS_ == K_TMEM && W_ == 1) {                                                             \
             if (use_tc(T)) return occupancy_sa<W_, KS_, NW_, MB_, FGD_TC>(strict, arm, smem);                 \
         }                                                                                                     \
         return occupancy_sa<W_, KS_, NW_, MB_, 0>(strict, arm, smem);                                         \
@@ -447,7 +447,7 @@ int fgd_create(const FgdConfig *cfg, FgdHandle **out)
     // operand table KD[k][thread][2R]: the R row entries K[t][k] then the R entries dK[t][k] of the team thread's rows
     // t = R*thread + r, and KO[k][thread][R]: the K entries alone (dense half of the backward contraction)
     const int nthr = h->TP / R;
-    std::vector<float> kd((size_t)T * 2 * h->TP, 0.0f), ko((size_t)T * h->TP, 0.0f);
+    std::vector<float> kd((size_t)T * 2 * h->TP, 0.0f), ko((size_t)T * h->TP, 0.0f), dko((size_t)T * h->TP, 0.0f);
     for (int k = 0; k < T; ++k)
         for (int i = 0; i < T; ++i) {
             const int thr = i / R, r = i % R;
@@ -455,11 +455,14 @@ int fgd_create(const FgdConfig *cfg, FgdHandle **out)
             kd[base + r] = cfg->h_km[i * T + k];
             kd[base + R + r] = cfg->h_dkm[i * T + k];
             ko[((size_t)k * nthr + thr) * R + r] = cfg->h_km[i * T + k];
+            dko[((size_t)k * nthr + thr) * R + r] = cfg->h_dkm[i * T + k];
         }
     CKC(cudaMalloc(&h->d_KD, kd.size() * 4));
     CKC(cudaMemcpy(h->d_KD, kd.data(), kd.size() * 4, cudaMemcpyHostToDevice));
     CKC(cudaMalloc(&h->d_KO, ko.size() * 4));
     CKC(cudaMemcpy(h->d_KO, ko.data(), ko.size() * 4, cudaMemcpyHostToDevice));
+    CKC(cudaMalloc(&h->d_DO, dko.size() * 4));
+    CKC(cudaMemcpy(h->d_DO, dko.data(), dko.size() * 4, cudaMemcpyHostToDevice));
     {
         const size_t slot = (size_t)cfg->obstacle_capacity * 2 * 4;
         CKC(cudaMalloc(&h->d_obs_ring, FGD_OBS_RING * slot));
@@ -509,7 +512,7 @@ int fgd_create(const FgdConfig *cfg, FgdHandle **out)
     p.q_hi = cfg->joint_safety_limit * p.qmax;
     p.q_lo = cfg->joint_safety_limit * p.qmin;
     p.v_hi = cfg->joint_safety_limit * p.vmax;
-    p.KD = h->d_KD; p.KO = h->d_KO;
+    p.KD = h->d_KD; p.KO = h->d_KO; p.DO = h->d_DO;
     *out = h;
     return FGD_OK;
 }
@@ -518,7 +521,7 @@ int fgd_destroy(FgdHandle *h)
 {
     if (!h) return FGD_OK;
     cudaFree(h->d_init);
-    cudaFree(h->d_KD); cudaFree(h->d_KO); cudaFree(h->d_obs_ring); cudaFree(h->d_obs_meta); cudaFree(h->d_queue);
+    cudaFree(h->d_KD); cudaFree(h->d_KO); cudaFree(h->d_DO); cudaFree(h->d_obs_ring); cudaFree(h->d_obs_meta); cudaFree(h->d_queue);
     if (h->h_obs_stage) cudaFreeHost(h->h_obs_stage);
     if (h->h_meta_stage) cudaFreeHost(h->h_meta_stage);
     for (int i = 0; i < FGD_OBS_RING; ++i) if (h->stage_event[i]) cudaEventDestroy(h->stage_event[i]);

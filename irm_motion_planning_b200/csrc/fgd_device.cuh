@@ -45,6 +45,7 @@ struct DevParams {
     float oml, inv_T, w_avg, mean_q, inv_std, inv_std2, inv_vmax, inv_vmax2, q_hi, q_lo, v_hi, fT;
     const float *KD;         // [T][TP/2][4]: K[t][k], K[t+1][k], dK[t][k], dK[t+1][k] of team thread t/2 (zero padded rows >= T)
     const float *KO;         // [T][TP/2][2]: K entries only (dense half of the backward contraction)
+    const float *DO;         // [T][TP/2][2]: dK entries only (T > 128: K lives in tensor memory, dK streams from L2)
     const float *obs;        // [n_obs][2]
     float *alpha;            // [B][T][3]  final alpha rows are written here
     const float *alpha_in;   // [B][T][3]  initial alpha rows are read from here (== alpha for the in-place calls)
@@ -90,18 +91,21 @@ constexpr int XCH_WORDS = 56;
 template <int WPT>
 struct Team {
     int lane, wit, tl;       // lane in warp, warp in team, thread in team
+    int bar;                 // WPT > 1: named barrier of this team (several teams per CTA), 0 = the CTA barrier (one team per CTA)
     float *xch;
-    __device__ __forceinline__ Team(float *xch_)
+    __device__ __forceinline__ Team(float *xch_, int bar_ = 0)
     {
         lane = threadIdx.x & 31;
         wit = (WPT == 1) ? 0 : ((threadIdx.x >> 5) & (WPT - 1));
         tl = wit * 32 + lane;
+        bar = bar_;
         xch = xch_;
     }
     __device__ __forceinline__ void sync() const
     {
         if constexpr (WPT == 1) __syncwarp();
-        else __syncthreads();
+        else if (bar == 0) __syncthreads();
+        else asm volatile("bar.sync %0, %1;" ::"r"(bar), "n"(WPT * 32) : "memory");
     }
 };
 
@@ -282,6 +286,16 @@ __device__ __forceinline__ void tmem_wait2(unsigned (&r)[2])
 {
     asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r[0]), "+r"(r[1]) :: "memory");
 }
+__device__ __forceinline__ void tmem_ld8(unsigned ta, unsigned (&r)[8])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(ta));
+}
+__device__ __forceinline__ void tmem_wait8(unsigned (&r)[8])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]) :: "memory");
+}
 __device__ __forceinline__ f2 u2f2(unsigned a, unsigned b) { return make_float2(__uint_as_float(a), __uint_as_float(b)); }
 
 // Forward contraction with the operand table in TMEM: same terms, same order (k ascending, one fma per term) as
@@ -393,6 +407,145 @@ __device__ __forceinline__ void contract_back_tm(unsigned tk, int T, const float
         if ((m1 >> l) & 1u) dk_row(l * R + 1);
     }
     dk_row(T - 1);
+}
+
+// ---------------------------------------------------------------------------
+// Multi-warp teams (T > 64) with the tables in tensor memory: ONE 16-warp CTA per SM holds all 512 TMEM columns and its
+// 16 / WPT teams share them - warp w reads lane quadrant w % 4, which holds the entries of team thread
+// 32 (w % WPT) + lane for every team alike.  Reading the tables through the L1 / shared-memory pipe costs 4 wavefronts
+// per warp and column k (512 B) against 12 FMA-pipe cycles of arithmetic, i.e. 80 data-pipe cycles against 48 FMA cycles
+// per column over the SM's 16 warps: the contraction ran at ~60 % of the obstacle loop's efficiency (phase clocks,
+// profiles/r02f_phase_clocks_loaded.txt).  The TMEM read path is a different one.
+//   WPT = 2 (T <= 128): K and dK (4 columns per k = 4 T <= 512 columns) - contract_tm / contract_back_mw<4>.
+//   WPT = 4 (T <= 256): K alone (2 columns per k); dK streams from the compact table DO in L2, 2 wavefronts per warp
+//   and k, and only for the forward contraction and the flagged rows of the backward one.
+// Same terms in the same order as contract<> / contract_back<>: bit-identical results.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void contract_tm_k(unsigned tk, const float *__restrict__ dd, const int stride, int T, const float4 *__restrict__ x,
+                                              f2 (&y1)[3], f2 (&y2)[3])
+{
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { y1[a] = bc2(0.0f); y2[a] = bc2(0.0f); }
+    int k = 0;
+#pragma unroll 2
+    for (; k + 4 <= T; k += 4) {
+        unsigned r[8];
+        tmem_ld8(tk + 2 * k, r);
+        float2 dv[4];
+        float4 xa[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { dv[u] = __ldg(reinterpret_cast<const float2 *>(dd + (size_t)(k + u) * stride)); xa[u] = x[k + u]; }
+        tmem_wait8(r);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const f2 kk = u2f2(r[2 * u], r[2 * u + 1]), dk = mk2(dv[u].x, dv[u].y);
+            y1[0] = fma2(kk, bc2(xa[u].x), y1[0]);
+            y1[1] = fma2(kk, bc2(xa[u].y), y1[1]);
+            y1[2] = fma2(kk, bc2(xa[u].z), y1[2]);
+            y2[0] = fma2(dk, bc2(xa[u].x), y2[0]);
+            y2[1] = fma2(dk, bc2(xa[u].y), y2[1]);
+            y2[2] = fma2(dk, bc2(xa[u].z), y2[2]);
+        }
+    }
+    for (; k < T; ++k) {
+        unsigned r[2];
+        tmem_ld2(tk + 2 * k, r);
+        const float2 dv = __ldg(reinterpret_cast<const float2 *>(dd + (size_t)k * stride));
+        const float4 xa = x[k];
+        tmem_wait2(r);
+        const f2 kk = u2f2(r[0], r[1]), dk = mk2(dv.x, dv.y);
+        y1[0] = fma2(kk, bc2(xa.x), y1[0]);
+        y1[1] = fma2(kk, bc2(xa.y), y1[1]);
+        y1[2] = fma2(kk, bc2(xa.z), y1[2]);
+        y2[0] = fma2(dk, bc2(xa.x), y2[0]);
+        y2[1] = fma2(dk, bc2(xa.y), y2[1]);
+        y2[2] = fma2(dk, bc2(xa.z), y2[2]);
+    }
+}
+
+// Backward contraction, multi-warp teams, K from tensor memory (CPK columns per k: 4 = K and dK interleaved, 2 = K alone);
+// the flagged dK rows from tensor memory (CPK = 4) or from DO (CPK = 2).
+template <int WPT, int CPK>
+__device__ __forceinline__ void contract_back_mw(unsigned tk, const float *__restrict__ dd, int T, const float4 *__restrict__ xa_rows,
+                                                 const float4 *__restrict__ xb_rows, const unsigned (&nz)[WPT][R], f2 (&y1)[3], f2 (&y2)[3])
+{
+    constexpr int SO = WPT * 32 * R;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { y1[a] = bc2(0.0f); y2[a] = bc2(0.0f); }
+    int k = 0;
+    if constexpr (CPK == 2) {
+#pragma unroll 2
+        for (; k + 8 <= T; k += 8) {
+            unsigned r[16];
+            tmem_ld16(tk + 2 * k, r);
+            float4 xa[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) xa[u] = xa_rows[k + u];
+            tmem_wait16(r);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const f2 kk = u2f2(r[2 * u], r[2 * u + 1]);
+                y1[0] = fma2(kk, bc2(xa[u].x), y1[0]);
+                y1[1] = fma2(kk, bc2(xa[u].y), y1[1]);
+                y1[2] = fma2(kk, bc2(xa[u].z), y1[2]);
+            }
+        }
+    } else {
+#pragma unroll 2
+        for (; k + 4 <= T; k += 4) {
+            unsigned r[16];
+            tmem_ld16(tk + 4 * k, r);
+            float4 xa[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) xa[u] = xa_rows[k + u];
+            tmem_wait16(r);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const f2 kk = u2f2(r[4 * u], r[4 * u + 1]);
+                y1[0] = fma2(kk, bc2(xa[u].x), y1[0]);
+                y1[1] = fma2(kk, bc2(xa[u].y), y1[1]);
+                y1[2] = fma2(kk, bc2(xa[u].z), y1[2]);
+            }
+        }
+    }
+    for (; k < T; ++k) {
+        unsigned r[2];
+        tmem_ld2(tk + CPK * k, r);
+        const float4 xa = xa_rows[k];
+        tmem_wait2(r);
+        const f2 kk = u2f2(r[0], r[1]);
+        y1[0] = fma2(kk, bc2(xa.x), y1[0]);
+        y1[1] = fma2(kk, bc2(xa.y), y1[1]);
+        y1[2] = fma2(kk, bc2(xa.z), y1[2]);
+    }
+#pragma unroll
+    for (int w = 0; w < WPT; ++w) {
+        unsigned any = nz[w][0] | nz[w][1];
+        while (any) {                               // team-uniform: ascending thread, then ascending r = ascending k
+            const int l = __ffs(any) - 1;
+            any &= any - 1;
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr) {
+                if ((nz[w][rr] >> l) & 1u) {
+                    const int kz = (w * 32 + l) * R + rr;
+                    const float4 xb = xb_rows[kz];
+                    f2 dv;
+                    if constexpr (CPK == 4) {
+                        unsigned r[2];
+                        tmem_ld2(tk + 4 * kz + 2, r);
+                        tmem_wait2(r);
+                        dv = u2f2(r[0], r[1]);
+                    } else {
+                        const float2 t = __ldg(reinterpret_cast<const float2 *>(dd + (size_t)kz * SO));
+                        dv = mk2(t.x, t.y);
+                    }
+                    y2[0] = fma2(dv, bc2(xb.x), y2[0]);
+                    y2[1] = fma2(dv, bc2(xb.y), y2[1]);
+                    y2[2] = fma2(dv, bc2(xb.z), y2[2]);
+                }
+            }
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------

@@ -213,15 +213,18 @@ __device__ __forceinline__ void stage_constants(const DevParams &p, const SmemLa
     __syncthreads();
 }
 
-// K / dK operand table -> tensor memory (see fgd_device.cuh): warp 0 allocates TMEM_COLS columns, warps 0..3 write
-// the table into their lane quadrant (lane l, columns 4k..4k+3 = KD[k][l]), every warp gets the address of the
-// quadrant it may read.  CTA-uniform control flow; call once, before the main loop.
+// K / dK operand table -> tensor memory (see fgd_device.cuh): warp 0 allocates COLS columns, warps 0..3 write the table
+// into their lane quadrant, every warp gets the address of the quadrant it may read.  Quadrant q holds the entries of team
+// thread 32 (q % WPT) + lane: single-warp teams (WPT = 1) - the same 32 threads in every quadrant; multi-warp teams - warp
+// w of the CTA is warp w % WPT of its team.  CPK = 4: lane columns 4k..4k+3 = KD[k][thread] (K and dK of the thread's two
+// rows); CPK = 2: columns 2k, 2k+1 = KO[k][thread] (K alone).  CTA-uniform control flow; call once, before the main loop.
+template <int WPT, int CPK, int COLS>
 __device__ __forceinline__ unsigned tmem_stage_tables(const DevParams &p)
 {
     __shared__ unsigned tm_base;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tm_base)), "r"((unsigned)TMEM_COLS) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tm_base)), "r"((unsigned)COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -229,12 +232,34 @@ __device__ __forceinline__ unsigned tmem_stage_tables(const DevParams &p)
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const unsigned tk = tm_base + ((unsigned)((warp & 3) * 32) << 16);
     if (warp < 4) {
-        const float4 *src = reinterpret_cast<const float4 *>(p.KD) + lane;      // KD[k][lane][4], 32 lanes per k
+        constexpr int NT = WPT * 32;                                            // threads per team = table entries per k
+        const int thr = (warp & (WPT - 1)) * 32 + lane;
+        // batches of 8 columns: the loads of a batch are in flight together (a one-column loop exposes the L2 / HBM latency
+        // T times: ~15 us of every launch's prologue at T = 50)
+        constexpr int KB = 8;
 #pragma unroll 1
-        for (int k = 0; k < p.T; ++k) {
-            const float4 v = __ldg(src + (size_t)k * 32);
-            asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tk + 4 * k), "r"(__float_as_uint(v.x)),
-                         "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)), "r"(__float_as_uint(v.w)) : "memory");
+        for (int k0 = 0; k0 < p.T; k0 += KB) {
+            if constexpr (CPK == 4) {
+                const float4 *src = reinterpret_cast<const float4 *>(p.KD) + thr;   // KD[k][thread][4]
+                float4 v[KB];
+#pragma unroll
+                for (int u = 0; u < KB; ++u) v[u] = (k0 + u < p.T) ? __ldg(src + (size_t)(k0 + u) * NT) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int u = 0; u < KB; ++u)
+                    if (k0 + u < p.T)
+                        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tk + 4 * (k0 + u)), "r"(__float_as_uint(v[u].x)),
+                                     "r"(__float_as_uint(v[u].y)), "r"(__float_as_uint(v[u].z)), "r"(__float_as_uint(v[u].w)) : "memory");
+            } else {
+                const float2 *src = reinterpret_cast<const float2 *>(p.KO) + thr;   // KO[k][thread][2]
+                float2 v[KB];
+#pragma unroll
+                for (int u = 0; u < KB; ++u) v[u] = (k0 + u < p.T) ? __ldg(src + (size_t)(k0 + u) * NT) : make_float2(0.f, 0.f);
+#pragma unroll
+                for (int u = 0; u < KB; ++u)
+                    if (k0 + u < p.T)
+                        asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(tk + 2 * (k0 + u)), "r"(__float_as_uint(v[u].x)),
+                                     "r"(__float_as_uint(v[u].y)) : "memory");
+            }
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     }
@@ -245,12 +270,13 @@ __device__ __forceinline__ unsigned tmem_stage_tables(const DevParams &p)
 }
 
 // every warp of the CTA is done with the tables: give the columns back
+template <int COLS>
 __device__ __forceinline__ void tmem_release_tables(unsigned tk)
 {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if ((threadIdx.x >> 5) == 0)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tk & 0x0000ffffu), "r"((unsigned)TMEM_COLS) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tk & 0x0000ffffu), "r"((unsigned)COLS) : "memory");
 }
 
 // ---------------------------------------------------------------------------
@@ -336,8 +362,12 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
     static_assert(!LIVE || (WPT == 1 && !SP), "live obstacle updates: single-warp teams");
     static_assert(!SP || (WPT == 1 && MODE == 0 && NW == SPEC && SPEC <= 8), "speculative line search: BLS, single-warp replicas, one trajectory per CTA");
     static_assert(TC == 0 || KS == K_TMEM, "compile-time T: TMEM instances only");
-    static_assert(WPT == 1 || NW == WPT, "multi-warp teams own their CTA");
-    static_assert(KS != K_TMEM || (WPT == 1 && NW >= 4 && NW % 4 == 0), "TMEM tables: single-warp teams, whole lane quadrants");
+    static_assert(WPT == 1 || NW == WPT || KS == K_TMEM, "multi-warp teams own their CTA unless they share the tensor-memory tables");
+    static_assert(KS != K_TMEM || (NW >= 4 && NW % 4 == 0 && NW % WPT == 0 && (WPT == 1 || NW / WPT <= 15)), "TMEM tables: whole lane quadrants, whole teams, one named barrier per team");
+    // tensor-memory columns per k and in total: single-warp teams K and dK of T <= 64 (two CTAs per SM may be resident);
+    // multi-warp teams own the SM: WPT = 2 K and dK of T <= 128, WPT = 4 K alone of T <= 256
+    constexpr int CPK = (KS == K_TMEM && WPT == 4) ? 2 : 4;
+    constexpr int TM_COLS = WPT == 1 ? TMEM_COLS : 512;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int TEAMS = NW / WPT;
     const int T = TC > 0 ? TC : p.T;
@@ -352,12 +382,13 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
     const int team = (threadIdx.x >> 5) / WPT;
     if (live) sObs += (size_t)team * L.obs_pairs;
     float4 *XA = reinterpret_cast<float4 *>(sTeams + (size_t)team * L.team_bytes()), *XB = XA + L.x_rows;
-    const Team<WPT> G(reinterpret_cast<float *>(XB + L.x_rows));
+    const Team<WPT> G(reinterpret_cast<float *>(XB + L.x_rows), (WPT > 1 && NW > WPT) ? 1 + team : 0);
     const float *kd = (KS == K_SMEM ? sKD : p.KD) + G.tl * 2 * R;
     const float *ko = (KS == K_SMEM ? sKO : p.KO) + G.tl * R;
+    const float *dd = p.DO + G.tl * R;
     unsigned tk = 0;
-    if constexpr (KS == K_TMEM) tk = tmem_stage_tables(p);
-    (void)kd; (void)ko; (void)tk;
+    if constexpr (KS == K_TMEM) tk = tmem_stage_tables<WPT, CPK, TM_COLS>(p);
+    (void)kd; (void)ko; (void)dd; (void)tk;
     int n_obs_live = 0, cur_gen = -1, polled_at = -1, n_switch = 0;       // LIVE: the team's obstacle set and poll bookkeeping
     (void)n_obs_live; (void)cur_gen; (void)polled_at; (void)n_switch;
     __shared__ SpecScratch sp_mem;                                          // SPEC only (a few words)
@@ -389,7 +420,15 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
         if (!boot) {
             if (kind == K_IDLE) break;
             gsync();                                                                     // operands complete
-            if constexpr (KS == K_TMEM) {
+            if constexpr (KS == K_TMEM && WPT > 1) {                                             // multi-warp teams sharing the SM's tensor memory
+                if (kind != K_BACK) {
+                    if constexpr (CPK == 4) contract_tm<true, 0>(tk, T, XA, XA, y1, y2);
+                    else contract_tm_k(tk, dd, WPT * 32 * R, T, XA, y1, y2);
+                } else {
+                    load_nz<WPT>(G, nz);
+                    contract_back_mw<WPT, CPK>(tk, dd, T, XA, XB, nz, y1, y2);
+                }
+            } else if constexpr (KS == K_TMEM) {
                 if (kind != K_BACK) contract_tm<true, TC>(tk, T, XA, XA, y1, y2);                // forward: K x, dK x
                 else if constexpr (SP) {                                                         // the winner's gradient operands
                     const float4 *XAw = reinterpret_cast<const float4 *>(sTeams + (size_t)win * L.team_bytes());
@@ -602,7 +641,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
     if (p.dbg && blockIdx.x == 0 && (SP ? threadIdx.x == 0 : G.tl == 0) && pc[7] > 2)
         for (int i = 0; i < 8; ++i) p.dbg[i] = (int)(pc[i] >> 4);      // units of 16 cycles
 #endif
-    if constexpr (KS == K_TMEM) tmem_release_tables(tk);
+    if constexpr (KS == K_TMEM) tmem_release_tables<TM_COLS>(tk);
 }
 
 // ---------------------------------------------------------------------------
@@ -761,7 +800,8 @@ __global__ void __launch_bounds__(256) fgd_ffma_peak_kernel(int iters, float see
     if (r == 123456.789f) sink[0] = r;
 }
 
-// MUFU roofline probe: 8 independent rcp.approx chains per thread (x -> 1/x -> x ...), nothing else.
+// MUFU roofline probe: 8 independent chains x -> 1/x + 1 per thread (ptxas folds a bare rcp(rcp(x)) chain to x and drops
+// the loop; the FADD keeps it honest and costs 1/8 of a MUFU slot on another pipe).
 __global__ void __launch_bounds__(256) fgd_mufu_peak_kernel(int iters, float seed, float *sink)
 {
     float a[8];
@@ -772,7 +812,7 @@ __global__ void __launch_bounds__(256) fgd_mufu_peak_kernel(int iters, float see
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
 #pragma unroll
-            for (int u = 0; u < 8; ++u) a[u] = rcp<false>(a[u]);
+            for (int u = 0; u < 8; ++u) a[u] = rcp<false>(a[u]) + 1.0f;
         }
     }
     const float r = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));

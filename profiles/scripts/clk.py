@@ -1,7 +1,8 @@
 """Where does a lone trajectory spend its cycles?  Needs a -DFGD_PHASE_CLOCKS build of the library:
     nvcc <flags of irm_motion_planning_b200/build.py> -DFGD_PHASE_CLOCKS -o profiles/scripts/libfgd_clk.so irm_motion_planning_b200/csrc/fgd_api.cu
 CTA 0 / warp 0 accumulates clock64() per phase of the loop; run on the GPU box from the repo root.
-usage: python profiles/scripts/clk.py [spec_max_batch ...]     (one run per value: 0 = sequential line search, 592 = speculative)"""
+usage: python profiles/scripts/clk.py [spec_max_batch ...]     (one run per value: 0 = sequential line search, 592 = speculative)
+       CLK_RUNS="c3:2368,c5:4736" python profiles/scripts/clk.py 0   (workload:batch pairs; the clocks are those of CTA 0 / team 0 under that load)"""
 import ctypes as C
 import os
 import sys
@@ -18,7 +19,8 @@ from irm_motion_planning_b200.workloads import initial_alpha, make_workload    #
 names = ["fwd contract", "cost_phase", "decide+grad", "tail(fwd)", "back contract", "back post", "tail(back)", "trips"]
 for spec in [int(x) for x in sys.argv[1:]] or [0]:
     os.environ["FGD_SPEC_MAX_BATCH"] = str(spec)
-    for wlname, B in (("c2", 1), ("c1", 1)):
+    runs = [(w.split(":")[0], int(w.split(":")[1])) for w in os.environ.get("CLK_RUNS", "c2:1,c1:1").split(",")]
+    for wlname, B in runs:
         wl = make_workload(wlname, B=B)
         traj = Trajectory(wl.args)
         traj.set_obstacles(wl.obstacles)

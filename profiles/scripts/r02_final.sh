@@ -1,0 +1,15 @@
+#!/bin/bash
+# Final single-GPU evidence of a round: tests, the default bench line, its ncu launch list, --set full captures.
+TAG=${1:-r02h}
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -3 | tee gpurun_out/${TAG}_pytest.txt
+timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/${TAG}_bench_default.json 2> gpurun_out/${TAG}_bench_default.err
+echo "bench rc=$?"; tail -2 gpurun_out/${TAG}_bench_default.err
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${TAG}_bench_reference_arm.json 2> gpurun_out/${TAG}_bench_reference_arm.err
+echo "reference arm rc=$?"
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+# launch list of the same command (shorter run; a number printed under ncu is never a bench value)
+timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches_default.csv \
+  python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-parity --secondary c2,c3,c4 > gpurun_out/${TAG}_launches_default.log 2>&1
+echo "launch list rc=$?"
+bash profiles/scripts/r02_counters.sh ${TAG} c3:4096:full c5:65536:full

@@ -263,6 +263,39 @@ int wait_obstacles(FgdHandle *h, cudaStream_t st)
     return FGD_OK;
 }
 
+// one persistent launch of the optimiser (p is complete; its queue counter has been reset on `st`)
+int launch_one(FgdHandle *h, const DevParams &p, int mode, int B, bool live, bool spec, cudaStream_t st)
+{
+    Geometry g = geometry(h, B, p.n_obs);
+    const bool strict = h->cfg.strict_math != 0;
+    if (live) {         // always the tensor-memory layout: 16 single-warp teams per CTA, one CTA per SM
+        g.block = 16 * 32;
+        g.smem = (int)make_layout(h->T, h->TP, h->cfg.obstacle_capacity, K_TMEM, 16, 1, true).bytes();
+        g.grid = B < h->num_sms ? B : h->num_sms;
+    }
+    if (g.smem + 64 > h->max_smem_optin) return FGD_ERR_TOO_MANY_OBSTACLES;
+    if (spec) {
+        g.block = SPEC_WARPS * 32;
+        g.smem = (int)make_layout(h->T, h->TP, p.n_obs, K_TMEM, SPEC_WARPS, 1).bytes();
+        g.grid = B < 2 * h->num_sms ? B : 2 * h->num_sms;
+        CK(use_tc(p.T) ? (strict ? launch_spec<true, FGD_TC>(p, g.grid, (size_t)g.smem, st) : launch_spec<false, FGD_TC>(p, g.grid, (size_t)g.smem, st))
+                       : (strict ? launch_spec<true, 0>(p, g.grid, (size_t)g.smem, st) : launch_spec<false, 0>(p, g.grid, (size_t)g.smem, st)));
+        h->spec_launches += 1;
+    } else if (live) {
+        CK(use_tc(p.T) ? (strict ? launch_live<true, FGD_TC>(p, g.grid, (size_t)g.smem, st) : launch_live<false, FGD_TC>(p, g.grid, (size_t)g.smem, st))
+                       : (strict ? launch_live<true, 0>(p, g.grid, (size_t)g.smem, st) : launch_live<false, 0>(p, g.grid, (size_t)g.smem, st)));
+    } else
+        CK(dispatch_opt(h->variant, h->WPT, strict, h->cfg.whole_arm_cost != 0, p, g.grid, (size_t)g.smem, st));
+    h->launches += 1;
+    h->opt_launches += 1;
+    if (!live) {        // a live kernel copies what it needs and validates it against the slot header; it must not hold up the publisher
+        CK(cudaEventRecord(h->launch_event, st));
+        h->launch_event_pending = true;
+        h->slot_captured[h->obs_gen % FGD_OBS_RING] = true;
+    }
+    return FGD_OK;
+}
+
 // d_alpha_in != nullptr: a fresh run that reads the initial alpha rows from d_alpha_in, writes the results to d_alpha
 // and never reads the loop state (fgd_optimize_host_io).
 int run_optimize(FgdHandle *h, int mode, int B, float *d_alpha, const float *d_start, const float *d_goal, float *d_fstate,
@@ -282,37 +315,9 @@ int run_optimize(FgdHandle *h, int mode, int B, float *d_alpha, const float *d_s
         if (h->cfg.whole_arm_cost) return FGD_ERR_INVALID_ARGUMENT;
         p.poll_every = poll_every; p.switch_log = d_switch_log;
     }
-    Geometry g = geometry(h, B, p.n_obs);
-    if (live) {         // always the tensor-memory layout: 16 single-warp teams per CTA, one CTA per SM
-        g.block = 16 * 32;
-        g.smem = (int)make_layout(h->T, h->TP, h->cfg.obstacle_capacity, K_TMEM, 16, 1, true).bytes();
-        g.grid = B < h->num_sms ? B : h->num_sms;
-    }
-    if (g.smem + 64 > h->max_smem_optin) return FGD_ERR_TOO_MANY_OBSTACLES;
-    CK(cudaMemsetAsync(p.queue, 0, sizeof(unsigned), st));      // this launch's own counter (launches on other streams keep theirs)
     const bool spec = mode == 0 && h->WPT == 1 && h->variant == 0 && !h->cfg.whole_arm_cost && !live && B <= h->spec_max_batch;
-    if (spec) {
-        g.block = SPEC_WARPS * 32;
-        g.smem = (int)make_layout(h->T, h->TP, p.n_obs, K_TMEM, SPEC_WARPS, 1).bytes();
-        g.grid = B < 2 * h->num_sms ? B : 2 * h->num_sms;
-        const bool strict = h->cfg.strict_math != 0;
-        CK(use_tc(p.T) ? (strict ? launch_spec<true, FGD_TC>(p, g.grid, (size_t)g.smem, st) : launch_spec<false, FGD_TC>(p, g.grid, (size_t)g.smem, st))
-                       : (strict ? launch_spec<true, 0>(p, g.grid, (size_t)g.smem, st) : launch_spec<false, 0>(p, g.grid, (size_t)g.smem, st)));
-        h->spec_launches += 1;
-    } else if (live) {
-        const bool strict = h->cfg.strict_math != 0;
-        CK(use_tc(p.T) ? (strict ? launch_live<true, FGD_TC>(p, g.grid, (size_t)g.smem, st) : launch_live<false, FGD_TC>(p, g.grid, (size_t)g.smem, st))
-                       : (strict ? launch_live<true, 0>(p, g.grid, (size_t)g.smem, st) : launch_live<false, 0>(p, g.grid, (size_t)g.smem, st)));
-    } else
-        CK(dispatch_opt(h->variant, h->WPT, h->cfg.strict_math != 0, h->cfg.whole_arm_cost != 0, p, g.grid, (size_t)g.smem, st));
-    h->launches += 1;
-    h->opt_launches += 1;
-    if (!live) {        // a live kernel copies what it needs and validates it against the slot header; it must not hold up the publisher
-        CK(cudaEventRecord(h->launch_event, st));
-        h->launch_event_pending = true;
-        h->slot_captured[h->obs_gen % FGD_OBS_RING] = true;
-    }
-    return FGD_OK;
+    CK(cudaMemsetAsync(p.queue, 0, sizeof(unsigned), st));      // this launch's own counter (launches on other streams keep theirs)
+    return launch_one(h, p, mode, B, live, spec, st);
 }
 
 // Page-locked host memory is addressable from the device (unified addressing): returns the device alias of

@@ -702,6 +702,43 @@ __device__ __forceinline__ void obstacle_block(const float2 *__restrict__ obs, c
     }
 }
 
+// Software-pipelined form of the obstacle loop (end-effector cost): a PAIR of obstacles per stage.  obstacle_pair_head
+// computes the distances and issues the reciprocals of a pair, obstacle_pair_tail accumulates a pair; the loop runs the head
+// of pair p+1 before the tail of pair p, so the MUFU latency of a pair is covered by the independent arithmetic of the next
+// one even for a lone warp (in the block form the accumulation stage waits for the reciprocals issued just before it:
+// `wait` was the top stall of the obstacle-bound shapes, FMA pipe 70 %).  Same operations, same ascending accumulation
+// order as obstacle_block<>: bit-identical.
+#ifndef FGD_OBS_PIPE
+#define FGD_OBS_PIPE 1
+#endif
+struct ObsPair { f2 dx[2], dy[2], rr[2]; };
+
+template <bool STRICT>
+__device__ __forceinline__ void obstacle_pair_head(const float2 *__restrict__ obs, const f2 x, const f2 y, ObsPair &P)
+{
+    const float4 a = *reinterpret_cast<const float4 *>(obs);
+    const float ox[2] = {a.x, a.z}, oy[2] = {a.y, a.w};
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        P.dx[u] = add2(x, bc2(-ox[u]));
+        P.dy[u] = add2(y, bc2(-oy[u]));
+        P.rr[u] = fma2(P.dy[u], P.dy[u], fma2(P.dx[u], P.dx[u], bc2(1.0f)));
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) P.rr[u] = mk2(rcp<STRICT>(P.rr[u].x), rcp<STRICT>(P.rr[u].y));
+}
+
+__device__ __forceinline__ void obstacle_pair_tail(const ObsPair &P, f2 &sr, f2 &sx, f2 &sy)
+{
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        sr = add2(sr, P.rr[u]);
+        const f2 r2 = mul2(P.rr[u], P.rr[u]);
+        sx = fma2(r2, P.dx[u], sx);
+        sy = fma2(r2, P.dy[u], sy);
+    }
+}
+
 // ---------------------------------------------------------------------------
 // Cost phase: compute_trajectory_cost + constraintsFulfilled for one trajectory
 // whose raw contraction rows are yq (K alpha) and yv (dK alpha).
@@ -765,15 +802,38 @@ __device__ __forceinline__ void cost_phase(const DevParams &p, const int T, cons
 #pragma unroll
     for (int j = 0; j < NJ; ++j) { sr[j] = bc2(0.0f); sx[j] = bc2(0.0f); sy[j] = bc2(0.0f); }
     int o = 0;
+    if constexpr (!ARM && FGD_OBS_PIPE) {
+        if (n_obs >= 2) {
+            ObsPair A, B;
+            obstacle_pair_head<STRICT>(sObs, px[2], py[2], A);
+            o = 2;
 #pragma unroll 1
-    for (; o + 4 <= n_obs; o += 4) {
+            for (; o + 4 <= n_obs; o += 4) {              // two pairs per trip so that A / B never have to be copied
+                obstacle_pair_head<STRICT>(sObs + o, px[2], py[2], B);
+                obstacle_pair_tail(A, sr[0], sx[0], sy[0]);
+                obstacle_pair_head<STRICT>(sObs + o + 2, px[2], py[2], A);
+                obstacle_pair_tail(B, sr[0], sx[0], sy[0]);
+            }
+            if (o + 2 <= n_obs) {
+                obstacle_pair_head<STRICT>(sObs + o, px[2], py[2], B);
+                obstacle_pair_tail(A, sr[0], sx[0], sy[0]);
+                obstacle_pair_tail(B, sr[0], sx[0], sy[0]);
+                o += 2;
+            } else {
+                obstacle_pair_tail(A, sr[0], sx[0], sy[0]);
+            }
+        }
+    } else {
+#pragma unroll 1
+        for (; o + 4 <= n_obs; o += 4) {
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) obstacle_block<4, STRICT>(sObs + o, px[3 - NJ + j], py[3 - NJ + j], sr[j], sx[j], sy[j]);
-    }
-    if (o + 2 <= n_obs) {
+            for (int j = 0; j < NJ; ++j) obstacle_block<4, STRICT>(sObs + o, px[3 - NJ + j], py[3 - NJ + j], sr[j], sx[j], sy[j]);
+        }
+        if (o + 2 <= n_obs) {
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) obstacle_block<2, STRICT>(sObs + o, px[3 - NJ + j], py[3 - NJ + j], sr[j], sx[j], sy[j]);
-        o += 2;
+            for (int j = 0; j < NJ; ++j) obstacle_block<2, STRICT>(sObs + o, px[3 - NJ + j], py[3 - NJ + j], sr[j], sx[j], sy[j]);
+            o += 2;
+        }
     }
     if (o < n_obs) {
 #pragma unroll

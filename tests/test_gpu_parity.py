@@ -704,3 +704,4 @@ def test_speculative_line_search_equals_sequential(cuda_ready, monkeypatch, T, B
             break
         a, fs, is_ = _gpu_optimize(tr, "bls", a, start, goal, budget=5, state=(fs, is_))
     assert np.array_equal(a.cpu().numpy(), ca) and np.array_equal(is_.cpu().numpy(), cis)
+

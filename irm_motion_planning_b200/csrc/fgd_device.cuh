@@ -707,7 +707,9 @@ __device__ __forceinline__ void obstacle_block(const float2 *__restrict__ obs, c
 // of pair p+1 before the tail of pair p, so the MUFU latency of a pair is covered by the independent arithmetic of the next
 // one even for a lone warp (in the block form the accumulation stage waits for the reciprocals issued just before it:
 // `wait` was the top stall of the obstacle-bound shapes, FMA pipe 70 %).  Same operations, same ascending accumulation
-// order as obstacle_block<>: bit-identical.
+// order as obstacle_block<>: bit-identical.  Used by the multi-warp-team kernels (T > 64): config 3 +9.4 %
+// (profiles/r02j_*); the single-warp-team kernels keep the block form, which measured 0.7 % (c2) to 3.7 % (c4, 256
+// obstacles) faster there and 0.5 % slower on c5.
 #ifndef FGD_OBS_PIPE
 #define FGD_OBS_PIPE 1
 #endif
@@ -802,7 +804,7 @@ __device__ __forceinline__ void cost_phase(const DevParams &p, const int T, cons
 #pragma unroll
     for (int j = 0; j < NJ; ++j) { sr[j] = bc2(0.0f); sx[j] = bc2(0.0f); sy[j] = bc2(0.0f); }
     int o = 0;
-    if constexpr (!ARM && FGD_OBS_PIPE) {
+    if constexpr (!ARM && WPT > 1 && FGD_OBS_PIPE) {
         if (n_obs >= 2) {
             ObsPair A, B;
             obstacle_pair_head<STRICT>(sObs, px[2], py[2], A);

@@ -707,9 +707,10 @@ __device__ __forceinline__ void obstacle_block(const float2 *__restrict__ obs, c
 // of pair p+1 before the tail of pair p, so the MUFU latency of a pair is covered by the independent arithmetic of the next
 // one even for a lone warp (in the block form the accumulation stage waits for the reciprocals issued just before it:
 // `wait` was the top stall of the obstacle-bound shapes, FMA pipe 70 %).  Same operations, same ascending accumulation
-// order as obstacle_block<>: bit-identical.  Used by the multi-warp-team kernels (T > 64): config 3 +9.4 %
-// (profiles/r02j_*); the single-warp-team kernels keep the block form, which measured 0.7 % (c2) to 3.7 % (c4, 256
-// obstacles) faster there and 0.5 % slower on c5.
+// order as obstacle_block<>: bit-identical.  Used (cost_phase<..., PIPE>) by the multi-warp-team kernels (T > 64): config 3
+// +9.4 % (profiles/r02j_*), and by the LIVE instance with runtime T.  The T = 50 instances keep the block form: at their
+// register pressure ptxas moves the tail of a pair right behind its own reciprocals again (seen in SASS), which measured
+// 0.7 % (c2) to 3.7 % (c4, 256 obstacles) slower than the block form.
 #ifndef FGD_OBS_PIPE
 #define FGD_OBS_PIPE 1
 #endif
@@ -750,7 +751,7 @@ __device__ __forceinline__ void obstacle_pair_tail(const ObsPair &P, f2 &sr, f2 
 // The obstacle loop accumulates sum 1/(2 den) and sum d/(2 den)^2; the constant factors
 // 0.8 and -0.8 of environment.py:43,57 (times 2 and 4) are applied once per sample.
 // ---------------------------------------------------------------------------
-template <int WPT, bool STRICT, bool ARM>
+template <int WPT, bool STRICT, bool ARM, bool PIPE = false>
 __device__ __forceinline__ void cost_phase(const DevParams &p, const int T, const float2 *__restrict__ sObs, const int n_obs, const Team<WPT> &G,
                                            const f2 (&yq)[3], const f2 (&yv)[3],
                                            const float *start, const float *goal, float lam_sg, float lam_jl,
@@ -804,7 +805,7 @@ __device__ __forceinline__ void cost_phase(const DevParams &p, const int T, cons
 #pragma unroll
     for (int j = 0; j < NJ; ++j) { sr[j] = bc2(0.0f); sx[j] = bc2(0.0f); sy[j] = bc2(0.0f); }
     int o = 0;
-    if constexpr (!ARM && WPT > 1 && FGD_OBS_PIPE) {
+    if constexpr (!ARM && PIPE && FGD_OBS_PIPE) {
         if (n_obs >= 2) {
             ObsPair A, B;
             obstacle_pair_head<STRICT>(sObs, px[2], py[2], A);

@@ -282,9 +282,7 @@ int launch_one(FgdHandle *h, const DevParams &p, int mode, int B, bool live, boo
                        : (strict ? launch_spec<true, 0>(p, g.grid, (size_t)g.smem, st) : launch_spec<false, 0>(p, g.grid, (size_t)g.smem, st)));
         h->spec_launches += 1;
     } else if (live) {
-        // many obstacles: the instance with runtime T, whose obstacle loop is software-pipelined (fgd_device.cuh)
-        static const bool force_tc = [] { const char *e = std::getenv("FGD_LIVE_FORCE_TC"); return e && e[0] == '1'; }();      // A/B measurements
-        CK(use_tc(p.T) && (p.n_obs < 64 || force_tc) ? (strict ? launch_live<true, FGD_TC>(p, g.grid, (size_t)g.smem, st) : launch_live<false, FGD_TC>(p, g.grid, (size_t)g.smem, st))
+        CK(use_tc(p.T) ? (strict ? launch_live<true, FGD_TC>(p, g.grid, (size_t)g.smem, st) : launch_live<false, FGD_TC>(p, g.grid, (size_t)g.smem, st))
                        : (strict ? launch_live<true, 0>(p, g.grid, (size_t)g.smem, st) : launch_live<false, 0>(p, g.grid, (size_t)g.smem, st)));
     } else
         CK(dispatch_opt(h->variant, h->WPT, strict, h->cfg.whole_arm_cost != 0, p, g.grid, (size_t)g.smem, st));

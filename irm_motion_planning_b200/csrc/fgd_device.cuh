@@ -708,9 +708,10 @@ __device__ __forceinline__ void obstacle_block(const float2 *__restrict__ obs, c
 // one even for a lone warp (in the block form the accumulation stage waits for the reciprocals issued just before it:
 // `wait` was the top stall of the obstacle-bound shapes, FMA pipe 70 %).  Same operations, same ascending accumulation
 // order as obstacle_block<>: bit-identical.  Used (cost_phase<..., PIPE>) by the multi-warp-team kernels (T > 64): config 3
-// +9.4 % (profiles/r02j_*), and by the LIVE instance with runtime T.  The T = 50 instances keep the block form: at their
-// register pressure ptxas moves the tail of a pair right behind its own reciprocals again (seen in SASS), which measured
-// 0.7 % (c2) to 3.7 % (c4, 256 obstacles) slower than the block form.
+// +9.4 % (profiles/r02j_*).  The single-warp-team kernels keep the block form: the pipelined loop measured 0.7 % (c2) to
+// 3.7 % (c4, 256 obstacles) slower in the T = 50 instances (at their register pressure ptxas moves the tail of a pair
+// right behind its own reciprocals again, seen in SASS) and 5.5 % slower in the runtime-T LIVE instance, where the
+// schedule survives (profiles/r02k_*).
 #ifndef FGD_OBS_PIPE
 #define FGD_OBS_PIPE 1
 #endif

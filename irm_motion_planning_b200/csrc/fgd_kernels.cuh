@@ -478,7 +478,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
             Rows<ARM> Rw;
             float loss_c, toc_c;
             int ful_c;
-            cost_phase<WPT, STRICT, ARM, (WPT > 1) || (LIVE && TC == 0)>(p, T, sObs, LIVE ? n_obs_live : p.n_obs, G, y1, y2, st.start, st.goal, st.lam_sg, st.lam_jl, Rw, loss_c, toc_c, ful_c);
+            cost_phase<WPT, STRICT, ARM, (WPT > 1)>(p, T, sObs, LIVE ? n_obs_live : p.n_obs, G, y1, y2, st.start, st.goal, st.lam_sg, st.lam_jl, Rw, loss_c, toc_c, ful_c);
             PCLK(1);
             bool accept = false;
             if (kind == K_EVAL0) {

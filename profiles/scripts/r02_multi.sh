@@ -14,7 +14,7 @@ run() {
 }
 run c5 --steps 5 --warmup 2
 run c2 --workload c2 --steps 10 --warmup 3 --no-parity
-NCCL_DEBUG=INFO timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus $N --steps 1 --warmup 1 --batch $((N*65536)) --no-e2e --no-parity 2>&1 | grep -E "NVLS|Connected all|via P2P|NET/" | sort | uniq -c | head -12 > gpurun_out/${TAG}_nccl_n$N.txt
+[ "$N" = "2" ] && NCCL_DEBUG=INFO timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus $N --steps 1 --warmup 1 --batch $((N*65536)) --no-e2e --no-parity 2>&1 | grep -E "NVLS|Connected all|via P2P|NET/" | sort | uniq -c | head -12 > gpurun_out/${TAG}_nccl_n$N.txt
 python - <<PY
 import json
 for n in ("c5","c2"):

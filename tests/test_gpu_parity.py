@@ -460,7 +460,7 @@ def _oracle_sweep_winners(cfs, cis, P, R):
 def test_config5_restart_sweep_pipeline_equals_oracle(cuda_ready):
     """Config 5 end to end on a small sweep (12 problems x 32 restarts): restart inputs -> optimise (strict) ->
     fgd_argmin_per_problem -> winners, against mirror optimise -> NumPy argmin: identical (cost, index, fulfilled).
-    Then the same sweep as two and as four restart-axis shards (what 2 / 4 ranks run), reduced by the elementwise min of
+    Then the same sweep as two, four and eight restart-axis shards (what 2 / 4 / 8 ranks run), reduced by the elementwise min of
     the order keys (what the all-gather feeds): identical winners, independent of the number of shards."""
     import torch
     from irm_motion_planning_b200.batch import BatchedFGD, decode_keys, restart_shard
@@ -482,13 +482,17 @@ def test_config5_restart_sweep_pipeline_equals_oracle(cuda_ready):
         keys = []
         for rank in range(world):
             lo, hi = restart_shard(R, rank, world)
-            a_s, s_s, g_s = initial_alpha(wl, tr, 4, restarts=(lo, hi))          # a rank generates only its block
-            assert np.array_equal(a_s, alpha0.reshape(P, R, 50, 3)[:, lo:hi].reshape(-1, 50, 3))
+            # the rank's block of the sweep (sliced from the full generation: a rank that generates only its block gets the
+            # same start / goal / via-offsets, but LAPACK's blocked solve may round a column differently for another nrhs)
+            blk = lambda x: np.ascontiguousarray(x.reshape((P, R) + x.shape[1:])[:, lo:hi].reshape((-1,) + x.shape[1:]))
+            a_s, s_s, g_s = blk(alpha0), blk(start), blk(goal)
+            _, s_gen, g_gen = initial_alpha(wl, tr, 4, restarts=(lo, hi))
+            assert np.array_equal(s_gen, s_s) and np.array_equal(g_gen, g_s)
             a, fs, is_ = _gpu_optimize(tr, "bls", a_s, s_s, g_s)
             keys.append(eng.best_keys(fs, is_, P, hi - lo, index_offset=lo, problem_stride=R))
         return decode_keys(torch.stack(keys).min(dim=0).values)
 
-    for world in (1, 2, 4):
+    for world in (1, 2, 4, 8):
         cost, idx, ful = run(world)
         assert np.array_equal(idx.cpu().numpy(), np.arange(P) * R + r_ref), world
         assert np.array_equal(cost.cpu().numpy(), c_ref), world

@@ -160,7 +160,8 @@ int fgd_optimize_gd(FgdHandle *h, int32_t B, float *d_alpha, const float *d_star
  * records it: int32 [B][FGD_SWITCH_LOG][2], entry 0 = (number of switches n, 0), entries 1..n = (inner iterations
  * completed, generation adopted) - replaying that schedule through the budgeted entry points (or the oracle)
  * reproduces the result bit for bit.  Single-warp teams only (n_timesteps <= 64): FGD_ERR_UNSUPPORTED_T otherwise;
- * FGD_ERR_TOO_MANY_OBSTACLES if obstacle_capacity x teams does not fit in shared memory. */
+ * FGD_ERR_TOO_MANY_OBSTACLES if obstacle_capacity x 16 teams does not fit in shared memory (capacity <= ~1500);
+ * FGD_ERR_INVALID_ARGUMENT for poll_every < 1 or a handle created with whole_arm_cost. */
 int fgd_optimize_live(FgdHandle *h, int32_t use_gd, int32_t B, float *d_alpha, const float *d_start, const float *d_goal,
                       float *d_fstate, int32_t *d_istate, int32_t poll_every, int32_t *d_switch_log, void *stream);
 

@@ -122,6 +122,38 @@ __device__ __forceinline__ float wmax(float v)
     for (int o = 16; o >= 1; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, o));
     return v;
 }
+// Maximum over the warp of NON-NEGATIVE, non-NaN floats: their bit patterns order like unsigned integers, so one
+// integer warp reduction (REDUX.MAX.U32) returns the bits of the maximum - the same value as the fmaxf butterfly.
+__device__ __forceinline__ float wmax_nonneg(float v)
+{
+    return __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(v)));
+}
+// Three warp sums at once, each bit-identical to wsum(): the xor butterfly adds the same pairs in every lane
+// (u_l = v_l + v_{l^16}, w_l = u_l + u_{l^8}, ...), so a lane only has to carry the partial of ONE value once the
+// halves of the warp split the work: after the 16-step lanes 0-15 carry a and b, lanes 16-31 carry c; after the 8-step
+// lanes 0-7 carry a, 8-15 b, 16-31 c; the 4-, 2- and 1-steps are plain butterflies and three index shuffles hand the
+// totals to every lane.  9 shuffles and 6 additions instead of 15 and 15.
+__device__ __forceinline__ void wsum3(float &a, float &b, float &c)
+{
+    const int lane = threadIdx.x & 31;
+    const bool lo = lane < 16, b3 = (lane & 8) != 0;
+    // 16-step
+    const float r1 = __shfl_xor_sync(FULL, lo ? c : a, 16);      // lo receives the partner's a, hi the partner's c
+    const float r2 = __shfl_xor_sync(FULL, b, 16);               // lo receives the partner's b
+    const float x1 = (lo ? a : c) + r1;
+    const float y1 = b + r2;                                     // meaningful in lanes 0-15
+    // 8-step: lanes 0-7 keep a and send b, lanes 8-15 keep b and send a, lanes 16-31 keep and send c
+    const bool keep_y = lo && b3;
+    const float keep = keep_y ? y1 : x1;
+    const float send = lo ? (b3 ? x1 : y1) : x1;
+    float z = keep + __shfl_xor_sync(FULL, send, 8);
+    z = z + __shfl_xor_sync(FULL, z, 4);
+    z = z + __shfl_xor_sync(FULL, z, 2);
+    z = z + __shfl_xor_sync(FULL, z, 1);
+    a = __shfl_sync(FULL, z, 0);
+    b = __shfl_sync(FULL, z, 8);
+    c = __shfl_sync(FULL, z, 16);
+}
 // cross-warp combination of warp partials p[0..WPT-1] in butterfly order
 template <int WPT>
 __device__ __forceinline__ float combine_sum(const float *p)
@@ -213,19 +245,24 @@ __device__ __forceinline__ float sqrt_norm(float x)
 // sin and cos of two angles: Cody-Waite reduction by pi/2 (3 constants) and the
 // cephes minimax polynomials on [-pi/4, pi/4]; <= 2 ulp for the angles a 3-joint
 // arm with limits [-1, 2] rad produces.  Same operation sequence as the oracle.
-__device__ __forceinline__ void quadrant(float j, float sn, float cs, float &S, float &C)
+// The quadrant index comes from the magic-number rounding t = fma(x, 2/pi, 1.5 * 2^23): the low mantissa bits of t
+// are round-to-nearest-even(x * 2/pi) in two's complement and j = t - 1.5 * 2^23 is that integer as a float - two
+// packed operations instead of an FRND and an F2I per angle and row (both quarter-rate).  Quadrant n = bits & 3:
+// swap sin / cos when n is odd, negate sin for n >= 2 (bit 1 of n), negate cos for n = 1, 2 (bit 1 of n + 1);
+// the negations are sign-bit flips done with integer logic.
+constexpr float SINCOS_MAGIC = 12582912.0f;       // 1.5 * 2^23
+__device__ __forceinline__ void quadrant(unsigned n, float sn, float cs, float &S, float &C)
 {
-    const int n = ((int)j) & 3;
-    S = (n & 1) ? cs : sn;
-    C = (n & 1) ? sn : cs;
-    if (n == 1 || n == 2) C = -C;
-    if (n >= 2) S = -S;
+    const bool sw = (n & 1u) != 0u;
+    const float s0 = sw ? cs : sn, c0 = sw ? sn : cs;
+    S = __uint_as_float(__float_as_uint(s0) ^ ((n << 30) & 0x80000000u));
+    C = __uint_as_float(__float_as_uint(c0) ^ (((n + 1u) << 30) & 0x80000000u));
 }
 
 __device__ __forceinline__ void sincos_cw2(f2 x, f2 &S, f2 &C)
 {
-    const f2 jj = mul2(x, bc2(6.366197467e-01f));
-    const f2 j = mk2(rintf(jj.x), rintf(jj.y));
+    const f2 t = fma2(x, bc2(6.366197467e-01f), bc2(SINCOS_MAGIC));
+    const f2 j = add2(t, bc2(-SINCOS_MAGIC));
     f2 r = fma2(j, bc2(-1.570796371e+00f), x);
     r = fma2(j, bc2(4.371138829e-08f), r);
     r = fma2(j, bc2(1.715124510e-15f), r);
@@ -236,8 +273,8 @@ __device__ __forceinline__ void sincos_cw2(f2 x, f2 &S, f2 &C)
     f2 pc = fma2(s, bc2(2.443315711809948e-5f), bc2(-1.388731625493765e-3f));
     pc = fma2(pc, s, bc2(4.166664568298827e-2f));
     const f2 cs = fma2(mul2(pc, s), s, fma2(bc2(-0.5f), s, bc2(1.0f)));
-    quadrant(j.x, sn.x, cs.x, S.x, C.x);
-    quadrant(j.y, sn.y, cs.y, S.y, C.y);
+    quadrant(__float_as_uint(t.x), sn.x, cs.x, S.x, C.x);
+    quadrant(__float_as_uint(t.y), sn.y, cs.y, S.y, C.y);
 }
 
 // where a kernel instance keeps the K / dK operand tables
@@ -851,7 +888,7 @@ __device__ __forceinline__ void cost_phase(const DevParams &p, const int T, cons
     if (valid0) { part_c = part_c + cost.x; lmax = fmaxf(lmax, cost.x); }
     if (valid1) { part_c = part_c + cost.y; lmax = fmaxf(lmax, cost.y); }
     // max / first argmax / sums over t: inside the warp, then across the warps of the team
-    float maxc = wmax(lmax);
+    float maxc = wmax_nonneg(lmax);                   // lmax >= +0 and never NaN (fmaxf drops a NaN cost): one REDUX instead of a butterfly
     // first sample of this warp that attains the maximum (trajectory.py:97 argmax = first index): two votes instead of a
     // second butterfly; lane l of the warp owns the samples t0w + 2l (slot x) and t0w + 2l + 1 (slot y)
     const unsigned bx = __ballot_sync(FULL, valid0 && cost.x == maxc), by = __ballot_sync(FULL, valid1 && cost.y == maxc);
@@ -859,7 +896,8 @@ __device__ __forceinline__ void cost_phase(const DevParams &p, const int T, cons
     int amax = 0x7fffffff;
     if (by) amax = t0w + (__ffs(by) - 1) * R + 1;
     if (bx) amax = min(amax, t0w + (__ffs(bx) - 1) * R);
-    float sum_c = wsum(part_c), sum_p = wsum(part_p), sum_v = wsum(part_v);
+    float sum_c = part_c, sum_p = part_p, sum_v = part_v;
+    wsum3(sum_c, sum_p, sum_v);
     bool all_ok = __all_sync(FULL, lim_ok);
     if constexpr (WPT == 1) {
         ssp0 = __shfl_sync(FULL, ssp0, 0);

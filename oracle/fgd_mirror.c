@@ -93,9 +93,15 @@ static void derive(const MirrorCfg *c, Derived *d)
 }
 
 /* ---- sin/cos ------------------------------------------------------------ */
+static inline uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+static inline float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+
 static void mirror_sincos(float x, float *s_out, float *c_out)
 {
-    float j = rintf(x * 6.366197467e-01f);             /* 2/pi */
+    /* magic-number rounding: the low mantissa bits of t = fma(x, 2/pi, 1.5 * 2^23) are round-to-nearest-even(x * 2/pi)
+     * in two's complement, j = t - 1.5 * 2^23 is that integer as a float (same sequence as the CUDA side) */
+    const float t = fmaf(x, 6.366197467e-01f, 12582912.0f);
+    const float j = t + -12582912.0f;
     float r = fmaf(j, -1.570796371e+00f, x);           /* Cody-Waite: pi/2 = C1+C2+C3 */
     r = fmaf(j, 4.371138829e-08f, r);
     r = fmaf(j, 1.715124510e-15f, r);
@@ -108,13 +114,10 @@ static void mirror_sincos(float x, float *s_out, float *c_out)
     float pc = fmaf(s, 2.443315711809948e-5f, -1.388731625493765e-3f);
     pc = fmaf(pc, s, 4.166664568298827e-2f);
     float cs = fmaf(pc * s, s, fmaf(-0.5f, s, 1.0f));
-    int n = ((int)j) & 3;
-    float S = (n & 1) ? cs : sn;
-    float C = (n & 1) ? sn : cs;
-    if (n == 1 || n == 2) C = -C;
-    if (n >= 2) S = -S;
-    *s_out = S;
-    *c_out = C;
+    const uint32_t n = f2u(t);                          /* quadrant = n & 3 */
+    const float s0 = (n & 1u) ? cs : sn, c0 = (n & 1u) ? sn : cs;
+    *s_out = u2f(f2u(s0) ^ ((n << 30) & 0x80000000u));          /* -sin for n & 3 >= 2 */
+    *c_out = u2f(f2u(c0) ^ (((n + 1u) << 30) & 0x80000000u));   /* -cos for n & 3 == 1, 2 */
 }
 
 /* ---- fixed-order reductions -------------------------------------------- */

@@ -789,7 +789,7 @@ __device__ __forceinline__ void obstacle_pair_tail(const ObsPair &P, f2 &sr, f2 
 // The obstacle loop accumulates sum 1/(2 den) and sum d/(2 den)^2; the constant factors
 // 0.8 and -0.8 of environment.py:43,57 (times 2 and 4) are applied once per sample.
 // ---------------------------------------------------------------------------
-template <int WPT, bool STRICT, bool ARM, bool PIPE = false>
+template <int WPT, bool STRICT, bool ARM, bool PIPE = false, bool OPAQUE_POS = false>
 __device__ __forceinline__ void cost_phase(const DevParams &p, const int T, const float2 *__restrict__ sObs, const int n_obs, const Team<WPT> &G,
                                            const f2 (&yq)[3], const f2 (&yv)[3],
                                            const float *start, const float *goal, float lam_sg, float lam_jl,
@@ -838,7 +838,14 @@ __device__ __forceinline__ void cost_phase(const DevParams &p, const int T, cons
         sspT = ss3(Rw.q[0].y - goal[0], Rw.q[1].y - goal[1], Rw.q[2].y - goal[2]);
         ssvT = ss3(Rw.v[0].y, Rw.v[1].y, Rw.v[2].y);
     }
-    // obstacle potential: both samples of this thread (at NJ joint positions) against every obstacle, in blocks of 4
+    // obstacle potential: both samples of this thread (at NJ joint positions) against every obstacle, in blocks of 4.
+    // OPAQUE_POS (the LIVE instance): the end-effector position passes through an own-lane shuffle first.  Without it ptxas
+    // re-derives px, py from the sines and cosines INSIDE the obstacle loop of that instance (4 extra FFMA2 per block of four
+    // obstacles to save four registers; config 4 was 6.7 % slower) - a shuffle result cannot be rematerialised.
+    if constexpr (OPAQUE_POS) {
+        px[2] = mk2(__shfl_sync(FULL, px[2].x, G.lane), __shfl_sync(FULL, px[2].y, G.lane));
+        py[2] = mk2(__shfl_sync(FULL, py[2].x, G.lane), __shfl_sync(FULL, py[2].y, G.lane));
+    }
     f2 sr[NJ], sx[NJ], sy[NJ];
 #pragma unroll
     for (int j = 0; j < NJ; ++j) { sr[j] = bc2(0.0f); sx[j] = bc2(0.0f); sy[j] = bc2(0.0f); }

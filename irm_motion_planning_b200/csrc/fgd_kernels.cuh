@@ -420,28 +420,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
         if (!boot) {
             if (kind == K_IDLE) break;
             gsync();                                                                     // operands complete
-            if constexpr (KS == K_TMEM && WPT > 1) {                                             // multi-warp teams sharing the SM's tensor memory
-                if (kind != K_BACK) {
-                    if constexpr (CPK == 4) contract_tm<true, 0>(tk, T, XA, XA, y1, y2);
-                    else contract_tm_k(tk, dd, WPT * 32 * R, T, XA, y1, y2);
-                } else {
-                    load_nz<WPT>(G, nz);
-                    contract_back_mw<WPT, CPK>(tk, dd, T, XA, XB, nz, y1, y2);
-                }
-            } else if constexpr (KS == K_TMEM) {
-                if (kind != K_BACK) contract_tm<true, TC>(tk, T, XA, XA, y1, y2);                // forward: K x, dK x
-                else if constexpr (SP) {                                                         // the winner's gradient operands
-                    const float4 *XAw = reinterpret_cast<const float4 *>(sTeams + (size_t)win * L.team_bytes());
-                    if (win != rep) { nz[0][0] = sp->nz[0]; nz[0][1] = sp->nz[1]; }
-                    contract_back_tm<TC>(tk, T, XAw, XAw + L.x_rows, nz, y1, y2);
-                } else contract_back_tm<TC>(tk, T, XA, XB, nz, y1, y2);                          // backward: K G_q + dK (-G_v)
-            } else {
-                if (kind != K_BACK) contract<WPT, KS, true>(kd, T, XA, XA, y1, y2);
-                else { load_nz<WPT>(G, nz); contract_back<WPT, KS>(ko, kd, T, XA, XB, nz, y1, y2); }
-            }
-            gsync();                                                                     // operands consumed
         }
-        PCLK(was_back ? 4 : 0);
         TRACE("lane %d trip boot=%d kind=%d\n", threadIdx.x, (int)boot, kind);
         bool want_cand = false;     // write the next candidate into XA
         bool want_head = false;     // go to the head of the inner loop
@@ -449,6 +428,22 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
         bool want_eval = false;     // (re-)evaluate loss and gradient operands at alpha
 
         if (!boot && kind == K_BACK) {
+            // ---- backward contraction: K G_q + dK (-G_v) ---------------------------------------
+            if constexpr (KS == K_TMEM && WPT > 1) {                                             // multi-warp teams sharing the SM's tensor memory
+                load_nz<WPT>(G, nz);
+                contract_back_mw<WPT, CPK>(tk, dd, T, XA, XB, nz, y1, y2);
+            } else if constexpr (KS == K_TMEM) {
+                if constexpr (SP) {                                                              // the winner's gradient operands
+                    const float4 *XAw = reinterpret_cast<const float4 *>(sTeams + (size_t)win * L.team_bytes());
+                    if (win != rep) { nz[0][0] = sp->nz[0]; nz[0][1] = sp->nz[1]; }
+                    contract_back_tm<TC>(tk, T, XAw, XAw + L.x_rows, nz, y1, y2);
+                } else contract_back_tm<TC>(tk, T, XA, XB, nz, y1, y2);
+            } else {
+                load_nz<WPT>(G, nz);
+                contract_back<WPT, KS>(ko, kd, T, XA, XB, nz, y1, y2);
+            }
+            gsync();                                                                     // operands consumed
+            PCLK(4);
             // ---- alpha-gradient, normalisation, first candidate ------------------------------
             f2 g[3];
             backward_rows(p, y1, y2, g);
@@ -474,11 +469,22 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
             want_cand = true;
             kind = K_CAND;
         } else if (!boot) {
+            // ---- forward contraction: K x, dK x for x = alpha or a candidate -------------------
+            if constexpr (KS == K_TMEM && WPT > 1) {
+                if constexpr (CPK == 4) contract_tm<true, 0>(tk, T, XA, XA, y1, y2);
+                else contract_tm_k(tk, dd, WPT * 32 * R, T, XA, y1, y2);
+            } else if constexpr (KS == K_TMEM) {
+                contract_tm<true, TC>(tk, T, XA, XA, y1, y2);
+            } else {
+                contract<WPT, KS, true>(kd, T, XA, XA, y1, y2);
+            }
+            gsync();                                                                     // operands consumed
+            PCLK(0);
             // ---- loss (and, if accepted, gradient operands) at alpha or at a candidate -------
             Rows<ARM> Rw;
             float loss_c, toc_c;
             int ful_c;
-            cost_phase<WPT, STRICT, ARM, (WPT > 1)>(p, T, sObs, LIVE ? n_obs_live : p.n_obs, G, y1, y2, st.start, st.goal, st.lam_sg, st.lam_jl, Rw, loss_c, toc_c, ful_c);
+            cost_phase<WPT, STRICT, ARM, (WPT > 1), LIVE>(p, T, sObs, LIVE ? n_obs_live : p.n_obs, G, y1, y2, st.start, st.goal, st.lam_sg, st.lam_jl, Rw, loss_c, toc_c, ful_c);
             PCLK(1);
             bool accept = false;
             if (kind == K_EVAL0) {

@@ -781,6 +781,41 @@ __device__ __forceinline__ void obstacle_pair_tail(const ObsPair &P, f2 &sr, f2 
 }
 
 // ---------------------------------------------------------------------------
+// Shared obstacle loop of single-warp teams.  A trajectory of T <= 64 samples keeps n_act = ceil(T / 2) lanes busy;
+// the other n_help = 32 - n_act lanes of its warp execute every instruction for nothing (T = 50: 7 of 32).  The
+// obstacle loop is the one phase whose work per sample is divisible, so with many obstacles it is shared: the owner
+// lane sums the obstacles [0, S), a helper lane sums the tail [S, n_obs) of up to k = ceil(n_act / n_help) owners one
+// after the other (positions and partial sums travel through the team's operand buffers, which are idle during the cost
+// phase), and the owner adds the helper's partial to its own: sr = srA + srB, sx = sxA + sxB, sy = syA + syB - each chain
+// in ascending obstacle order from zero.  S = k * Lseg with Lseg = 4 * ceil(n_obs / (4 (k + 1))), so that k owner
+// segments and one tail are equally long: T = 50, 256 obstacles: k = 4, S = 208, tail 48 - 208 loop steps per lane
+// instead of 256.  The split is part of the documented summation order (the mirror oracle follows it) whenever
+// share_split() > 0: single-warp teams, end-effector cost, at least FGD_SHARE_MIN_OBS obstacles.  Instances without the
+// helper code (HELP = false) evaluate both chains in the owner lane - same bits.
+// ---------------------------------------------------------------------------
+constexpr int FGD_SHARE_MIN_OBS = 64;
+__host__ __device__ inline int share_split(int T, int n_obs, bool whole_arm)
+{
+    if (T > 64 || whole_arm || n_obs < FGD_SHARE_MIN_OBS) return 0;
+    const int n_act = (T + 1) / 2, n_help = 32 - n_act;
+    if (n_help <= 0) return 0;
+    const int k = (n_act + n_help - 1) / n_help;
+    const int lseg = 4 * ((n_obs + 4 * (k + 1) - 1) / (4 * (k + 1)));
+    const int S = k * lseg;
+    return S < n_obs ? S : 0;
+}
+
+// obstacles [o0, o1) against the row pair at (x, y), ascending, block form (o0 even)
+template <bool STRICT>
+__device__ __forceinline__ void obstacle_range(const float2 *__restrict__ sObs, int o0, const int o1, const f2 x, const f2 y, f2 &sr, f2 &sx, f2 &sy)
+{
+#pragma unroll 1
+    for (; o0 + 4 <= o1; o0 += 4) obstacle_block<4, STRICT>(sObs + o0, x, y, sr, sx, sy);
+    if (o0 + 2 <= o1) { obstacle_block<2, STRICT>(sObs + o0, x, y, sr, sx, sy); o0 += 2; }
+    if (o0 < o1) obstacle_block<1, STRICT>(sObs + o0, x, y, sr, sx, sy);
+}
+
+// ---------------------------------------------------------------------------
 // Cost phase: compute_trajectory_cost + constraintsFulfilled for one trajectory
 // whose raw contraction rows are yq (K alpha) and yv (dK alpha).
 //   trajectory.py:271-281 (total), :81-88 (max/mean), :183-255 (penalties),
@@ -789,11 +824,14 @@ __device__ __forceinline__ void obstacle_pair_tail(const ObsPair &P, f2 &sr, f2 
 // The obstacle loop accumulates sum 1/(2 den) and sum d/(2 den)^2; the constant factors
 // 0.8 and -0.8 of environment.py:43,57 (times 2 and 4) are applied once per sample.
 // ---------------------------------------------------------------------------
-template <int WPT, bool STRICT, bool ARM, bool PIPE = false, bool OPAQUE_POS = false>
+// split: share_split() of this launch / obstacle set (0: one chain per sample); HELP: the tail chain runs on the helper
+// lanes, XA / XB = the team's operand buffers as scratch.
+template <int WPT, bool STRICT, bool ARM, bool PIPE = false, bool OPAQUE_POS = false, bool HELP = false>
 __device__ __forceinline__ void cost_phase(const DevParams &p, const int T, const float2 *__restrict__ sObs, const int n_obs, const Team<WPT> &G,
                                            const f2 (&yq)[3], const f2 (&yv)[3],
                                            const float *start, const float *goal, float lam_sg, float lam_jl,
-                                           Rows<ARM> &Rw, float &loss, float &toc, int &ful)
+                                           Rows<ARM> &Rw, float &loss, float &toc, int &ful,
+                                           const int split = 0, float4 *XA = nullptr, float4 *XB = nullptr)
 {
     constexpr int NJ = ARM ? 3 : 1;                        // joint positions charged with the obstacle potential
     const int t0 = G.tl * R;
@@ -850,7 +888,43 @@ __device__ __forceinline__ void cost_phase(const DevParams &p, const int T, cons
 #pragma unroll
     for (int j = 0; j < NJ; ++j) { sr[j] = bc2(0.0f); sx[j] = bc2(0.0f); sy[j] = bc2(0.0f); }
     int o = 0;
-    if constexpr (!ARM && PIPE && FGD_OBS_PIPE) {
+    if (!ARM && WPT == 1 && split > 0) {                   // warp-uniform: two chains per sample (see share_split)
+        if constexpr (!ARM && WPT == 1 && HELP) {
+            const int n_act = (T + 1) >> 1, n_help = 32 - n_act, k = (n_act + n_help - 1) / n_help, lseg = split / k;
+            const bool helper = G.lane >= n_act;
+            if (!helper) XA[G.lane] = make_float4(px[2].x, px[2].y, py[2].x, py[2].y);
+            __syncwarp();
+            f2 x = px[2], y = py[2];
+#pragma unroll 1
+            for (int j = 0; j < k; ++j) {
+                int o0 = j * lseg, o1 = o0 + lseg, own = -1;
+                if (helper) {                              // tail of owner `own`, a fresh chain
+                    own = (G.lane - n_act) + j * n_help;
+                    const float4 pq = XA[own < n_act ? own : 0];
+                    x = mk2(pq.x, pq.y); y = mk2(pq.z, pq.w);
+                    sr[0] = bc2(0.0f); sx[0] = bc2(0.0f); sy[0] = bc2(0.0f);
+                    o0 = split; o1 = own < n_act ? n_obs : split;
+                }
+                obstacle_range<STRICT>(sObs, o0, o1, x, y, sr[0], sx[0], sy[0]);
+                if (helper && own < n_act) {
+                    XA[own] = make_float4(sr[0].x, sr[0].y, sx[0].x, sx[0].y);
+                    XB[own] = make_float4(sy[0].x, sy[0].y, 0.0f, 0.0f);
+                }
+            }
+            __syncwarp();
+            if (!helper) {
+                const float4 r0 = XA[G.lane], r1 = XB[G.lane];
+                sr[0] = add2(sr[0], mk2(r0.x, r0.y)); sx[0] = add2(sx[0], mk2(r0.z, r0.w)); sy[0] = add2(sy[0], mk2(r1.x, r1.y));
+            }
+            __syncwarp();                                  // the scratch rows are free again
+        } else {
+            f2 tr = bc2(0.0f), tx = bc2(0.0f), ty = bc2(0.0f);
+            obstacle_range<STRICT>(sObs, 0, split, px[2], py[2], sr[0], sx[0], sy[0]);
+            obstacle_range<STRICT>(sObs, split, n_obs, px[2], py[2], tr, tx, ty);
+            sr[0] = add2(sr[0], tr); sx[0] = add2(sx[0], tx); sy[0] = add2(sy[0], ty);
+        }
+        o = n_obs;
+    } else if constexpr (!ARM && PIPE && FGD_OBS_PIPE) {
         if (n_obs >= 2) {
             ObsPair A, B;
             obstacle_pair_head<STRICT>(sObs, px[2], py[2], A);

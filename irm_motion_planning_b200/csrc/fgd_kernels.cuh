@@ -391,6 +391,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
     (void)kd; (void)ko; (void)dd; (void)tk;
     int n_obs_live = 0, cur_gen = -1, polled_at = -1, n_switch = 0;       // LIVE: the team's obstacle set and poll bookkeeping
     (void)n_obs_live; (void)cur_gen; (void)polled_at; (void)n_switch;
+    int split = LIVE ? 0 : share_split(T, p.n_obs, ARM);                  // two-chain obstacle sums (fgd_device.cuh, share_split); LIVE: follows the adopted set
     __shared__ SpecScratch sp_mem;                                          // SPEC only (a few words)
     SpecScratch *sp = &sp_mem;
     const int rep = SP ? (int)(threadIdx.x >> 5) : 0;                       // replica index = candidate offset in a round
@@ -484,7 +485,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
             Rows<ARM> Rw;
             float loss_c, toc_c;
             int ful_c;
-            cost_phase<WPT, STRICT, ARM, (WPT > 1), LIVE>(p, T, sObs, LIVE ? n_obs_live : p.n_obs, G, y1, y2, st.start, st.goal, st.lam_sg, st.lam_jl, Rw, loss_c, toc_c, ful_c);
+            cost_phase<WPT, STRICT, ARM, (WPT > 1), LIVE, LIVE>(p, T, sObs, LIVE ? n_obs_live : p.n_obs, G, y1, y2, st.start, st.goal, st.lam_sg, st.lam_jl, Rw, loss_c, toc_c, ful_c,
+                                                                split, XA, XB);
             PCLK(1);
             bool accept = false;
             if (kind == K_EVAL0) {
@@ -585,6 +587,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
                     if (st.inner_total != polled_at && st.inner_total % p.poll_every == 0) {
                         polled_at = st.inner_total;
                         switched = live_refresh(p, G.lane, sObs, cur_gen, n_obs_live);
+                        split = share_split(T, n_obs_live, false);
                         if (switched) log_switch(p, G.lane, st.traj, n_switch, st.inner_total, cur_gen);
                     }
                 }
@@ -617,6 +620,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
             if constexpr (LIVE) {
                 if (kind != K_IDLE) {                          // a trajectory starts with the latest obstacle set
                     live_refresh(p, G.lane, sObs, cur_gen, n_obs_live);
+                    split = share_split(T, n_obs_live, false);
                     n_switch = 0; polled_at = st.inner_total;
                     log_switch(p, G.lane, st.traj, n_switch, st.inner_total, cur_gen);
                 }
@@ -690,7 +694,7 @@ __global__ void __launch_bounds__(NW * 32) fgd_eval_kernel(const __grid_constant
         Rows<ARM> Rw;
         float loss, toc;
         int ful;
-        cost_phase<WPT, STRICT, ARM>(p, T, sObs, p.n_obs, G, y1, y2, start, goal, e.lam_sg, e.lam_jl, Rw, loss, toc, ful);
+        cost_phase<WPT, STRICT, ARM>(p, T, sObs, p.n_obs, G, y1, y2, start, goal, e.lam_sg, e.lam_jl, Rw, loss, toc, ful, share_split(T, p.n_obs, ARM));
         if (G.tl == 0) {
             if (e.loss) e.loss[b] = loss;
             if (e.toc) e.toc[b] = toc;

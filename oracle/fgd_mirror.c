@@ -128,6 +128,20 @@ static void mirror_sincos(float x, float *s_out, float *c_out)
  * CUDA side (csrc/fgd_device.cuh).                                                         */
 static int warps_per_trajectory(int T) { return T <= 64 ? 1 : (T <= 128 ? 2 : (T <= 256 ? 4 : 8)); }
 
+/* Obstacle sums of single-warp teams with many obstacles are TWO chains per sample, [0, S) and [S, n_obs), each in
+ * ascending order from zero, added at the end (csrc/fgd_device.cuh, share_split: the tail chain runs on the lanes of the
+ * warp that own no sample).  0 = one chain. */
+static int share_split(int T, int n_obs, int whole_arm)
+{
+    if (T > 64 || whole_arm || n_obs < 64) return 0;
+    const int n_act = (T + 1) / 2, n_help = 32 - n_act;
+    if (n_help <= 0) return 0;
+    const int k = (n_act + n_help - 1) / n_help;
+    const int lseg = 4 * ((n_obs + 4 * (k + 1) - 1) / (4 * (k + 1)));
+    const int S = k * lseg;
+    return S < n_obs ? S : 0;
+}
+
 static float tree_sum(const float *x, int T)
 {
     const int WPT = warps_per_trajectory(T);
@@ -204,9 +218,12 @@ static void evaluate_point(const MirrorCfg *c, const Derived *d, const float *K,
         float px[3], py[3], cj[3], srj[3];                           /* joint positions fk_1, fk_2, fk_3 = fk   robot.py:33-34, 39-72 */
         px[0] = c->link[0] * cs[t][0]; px[1] = fmaf(c->link[1], cs[t][1], px[0]); px[2] = fmaf(c->link[2], cs[t][2], px[1]);
         py[0] = c->link[0] * sn[t][0]; py[1] = fmaf(c->link[1], sn[t][1], py[0]); py[2] = fmaf(c->link[2], sn[t][2], py[1]);
+        const int split = share_split(T, c->n_obs, c->whole_arm);
         for (int j = j_lo; j < 3; ++j) {
             float sr = 0.0f, sx = 0.0f, sy = 0.0f;
+            float hr = 0.0f, hx = 0.0f, hy = 0.0f;           /* the chain before the split point */
             for (int o = 0; o < c->n_obs; ++o) {             /* environment.py:46-58 */
+                if (split > 0 && o == split) { hr = sr; hx = sx; hy = sy; sr = 0.0f; sx = 0.0f; sy = 0.0f; }
                 float dx = px[j] - obs[2 * o], dy = py[j] - obs[2 * o + 1];
                 float m = fmaf(dy, dy, fmaf(dx, dx, 1.0f));  /* 2 den = 1 + |f-o|^2  */
                 float r = 1.0f / m;
@@ -215,6 +232,7 @@ static void evaluate_point(const MirrorCfg *c, const Derived *d, const float *K,
                 sx = fmaf(r2, dx, sx);                       /* sum d/(2 den)^2      */
                 sy = fmaf(r2, dy, sy);
             }
+            if (split > 0) { sr = hr + sr; sx = hx + sx; sy = hy + sy; }
             srj[j] = sr; cj[j] = 1.6f * sr; gx[t][j] = -3.2f * sx; gy[t][j] = -3.2f * sy;
         }
         /* whole arm: c_1 + c_2 + c_3 as fma(1.6, s_3, fma(1.6, s_2, 1.6 * s_1)) */

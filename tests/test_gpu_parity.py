@@ -60,7 +60,8 @@ def _gpu_optimize(tr, mode, alpha0, start, goal, budget=-1, state=None):
     return a, fs, is_
 
 
-@pytest.mark.parametrize("T,n_obs", [(50, 11), (20, 11), (33, 37), (64, 5), (65, 9), (100, 64), (129, 20), (256, 300)])
+@pytest.mark.parametrize("T,n_obs", [(50, 11), (20, 11), (33, 37), (64, 5), (65, 9), (100, 64), (129, 20), (256, 300),
+                                     (50, 256), (50, 67), (33, 100), (20, 64), (63, 130), (64, 200)])      # >= 64 obstacles, T < 64: two-chain obstacle sums (share_split)
 def test_eval_bit_exact_strict(cuda_ready, T, n_obs):
     args, tr, obs, start, goal, alpha0 = _setup(T=T, n_obs=n_obs, B=24, seed=T)
     rng = np.random.default_rng(T + 1)
@@ -118,6 +119,8 @@ def test_eval_lambda_max_override(cuda_ready):
     ("bls", 4, 129, 17, 24, {"max_inner_iteration": 20, "max_outer_iteration": 2}),
     ("gd", 4, 200, 64, 20, {"max_inner_iteration": 15, "max_outer_iteration": 1}),
     ("bls", 1, 50, 11, 64, {"constraint_violating_dependant_loss": False, "lambda_max_cost": 0.25}),
+    ("bls", 1, 50, 300, 40, {"max_inner_iteration": 30, "max_outer_iteration": 2}),      # two-chain obstacle sums (share_split)
+    ("gd", 1, 33, 101, 30, {"max_inner_iteration": 30, "max_outer_iteration": 2}),
 ])
 def test_optimize_bit_exact_strict(cuda_ready, mode, wpt, T, n_obs, B, over):
     """Whole optimisation (all outer / inner / line-search iterations) bit-identical to the oracle:

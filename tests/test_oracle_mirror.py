@@ -254,3 +254,27 @@ def test_fast_mode_division_by_T_equals_ieee_division():
             rem = rn(Fraction(float(x)) - Fraction(float(q0)) * Fraction(float(y)))
             q1 = rn(Fraction(float(rem)) * Fraction(float(r)) + Fraction(float(q0)))
             assert q1 == np.float32(x / y), (T, x)
+
+
+@pytest.mark.parametrize("T,n_obs", [(50, 256), (50, 67), (33, 100), (20, 64)])
+def test_two_chain_obstacle_sums_match_numpy_oracle(T, n_obs):
+    """Single-warp teams with >= 64 obstacles sum the potential of a sample as two chains, [0, S) and [S, n_obs)
+    (csrc/fgd_device.cuh share_split; the tail chain runs on the warp's sample-less lanes).  A re-association like the
+    butterfly sums: the mirror stays within the per-evaluation tolerance of the FP64 NumPy oracle (loss rel <= 2e-6,
+    gradient rel <= 5e-6), and the split point is where the kernel puts it."""
+    hp = O.Hyper(n_timesteps=T)
+    tm64, tm32 = O.TrajectoryModel(hp, dtype=np.float64), O.TrajectoryModel(hp)
+    rng = np.random.default_rng(100 * T + n_obs)
+    obs = np.stack([rng.uniform(-3.0, 3.0, n_obs), rng.uniform(-3.0, 3.0, n_obs)], axis=1)
+    alpha = rng.standard_normal((T, 3)) * 0.05
+    s, g = np.array([0.1, -0.2, 0.3]), np.array([1.2, 1.0, 0.3])
+    loss = tm64.cost(alpha, obs, s, g, 0.5, 0.1, hp.lambda_max_cost)
+    G = tm64.cost_g(alpha, obs, s, g, 0.5, 0.1, hp.lambda_max_cost)
+    m = M.Mirror(hp, tm32.km, tm32.dkm, tm32.jac, obs.astype(np.float32), "bls")
+    e = m.eval(alpha.astype(np.float32)[None], s.astype(np.float32), g.astype(np.float32), 0.5, 0.1)
+    np.testing.assert_allclose(e["loss"][0], loss, rtol=2e-6)
+    assert _rel(e["grad"][0], G) < 5e-6
+    n_act = (T + 1) // 2
+    k = -(-n_act // (32 - n_act))
+    lseg = 4 * -(-n_obs // (4 * (k + 1)))
+    assert 0 < k * lseg < n_obs and (T, n_obs) != (50, 256) or k * lseg == 208

@@ -215,6 +215,37 @@ __device__ __forceinline__ float rcp(float x)
     }
 }
 
+// Reciprocals of U packed pairs m = 1 + |f - o|^2 (>= 1, or NaN).  Fast: MUFU.RCP.  Strict: the IEEE reciprocal.
+// __frcp_rn is MUFU.RCP + one Newton step (e = fma(r, m, -1), r' = fma(r, -e, r)) behind an exponent check that sends
+// m >= 2^126, infinities, NaNs, zeros and denormals to a slow path - per value: ~9 scalar instructions and a branch, which
+// made the strict obstacle loop 2.4x slower than the fast one.  Here m >= 1, so the only slow-path case is m >= 2^126:
+// ONE check per block (the maximum of the block's values) guards the same Newton step in packed form (two FFMA2 per pair,
+// the same operations as the fast path of __frcp_rn: bit-identical), a block with an absurdly distant obstacle takes
+// __frcp_rn.  Both branches return the correctly rounded reciprocal.
+template <int U, bool STRICT>
+__device__ __forceinline__ void rcp_block(f2 (&m)[U])
+{
+    if constexpr (!STRICT) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) m[u] = mk2(rcp<false>(m[u].x), rcp<false>(m[u].y));
+    } else {
+        float mx = fmaxf(m[0].x, m[0].y);
+#pragma unroll
+        for (int u = 1; u < U; ++u) mx = fmaxf(mx, fmaxf(m[u].x, m[u].y));
+        if (mx < 8.507059173e+37f) {                    // 2^126
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const f2 r = mk2(rcp<false>(m[u].x), rcp<false>(m[u].y));
+                const f2 e = fma2(r, m[u], bc2(-1.0f));
+                m[u] = fma2(r, neg2(e), r);
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < U; ++u) m[u] = mk2(__frcp_rn(m[u].x), __frcp_rn(m[u].y));
+        }
+    }
+}
+
 // x / T for the means over the time samples.  Strict: the IEEE division.  Fast: q0 = x * (1/T), one exact-remainder
 // correction (Markstein) - equal to the IEEE quotient for finite x (tests/test_oracle_mirror.py checks the sequence
 // against true division), 3 instructions instead of ~16 on the scalar critical path.
@@ -728,8 +759,7 @@ __device__ __forceinline__ void obstacle_block(const float2 *__restrict__ obs, c
         dy[u] = add2(y, bc2(-ob[u].y));
         rr[u] = fma2(dy[u], dy[u], fma2(dx[u], dx[u], bc2(1.0f)));
     }
-#pragma unroll
-    for (int u = 0; u < U; ++u) rr[u] = mk2(rcp<STRICT>(rr[u].x), rcp<STRICT>(rr[u].y));
+    rcp_block<U, STRICT>(rr);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         sr = add2(sr, rr[u]);
@@ -765,8 +795,7 @@ __device__ __forceinline__ void obstacle_pair_head(const float2 *__restrict__ ob
         P.dy[u] = add2(y, bc2(-oy[u]));
         P.rr[u] = fma2(P.dy[u], P.dy[u], fma2(P.dx[u], P.dx[u], bc2(1.0f)));
     }
-#pragma unroll
-    for (int u = 0; u < 2; ++u) P.rr[u] = mk2(rcp<STRICT>(P.rr[u].x), rcp<STRICT>(P.rr[u].y));
+    rcp_block<2, STRICT>(P.rr);
 }
 
 __device__ __forceinline__ void obstacle_pair_tail(const ObsPair &P, f2 &sr, f2 &sx, f2 &sy)

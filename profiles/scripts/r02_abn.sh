@@ -15,7 +15,7 @@ for lib in $LIBS; do
       c4) A="--workload c4 --batch 65536 --steps 2 --warmup 1";;
       c1) A="--workload c1 --steps 20 --warmup 5";;
     esac
-    timeout 600 python bench.py $A $B >> gpurun_out/${TAG}_${w}_$lib.json 2>> gpurun_out/${TAG}_${w}_$lib.err
+    timeout 600 python bench.py $A $B $EXTRA >> gpurun_out/${TAG}_${w}_$lib.json 2>> gpurun_out/${TAG}_${w}_$lib.err
   done
 done
 done

@@ -53,7 +53,7 @@ def parse(argv=None):
     ap.add_argument("--presoak-seconds", type=float, default=1.0,
                     help="untimed repetitions of the step before the W warm-up steps, so that the GPU has left its idle clocks")
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary workloads of the default single-GPU run")
-    ap.add_argument("--secondary", default="c2,c2sat,c3,c4", help="secondary workloads of the default single-GPU run")
+    ap.add_argument("--secondary", default="c2,c2sat,c3,c4,c1,c5_strict", help="secondary workloads of the default single-GPU run")
     ap.add_argument("--c4-relaunch", action="store_true", help="c4 through one launch per 8 iterations (round-1 path) instead of the live kernel")
     return ap.parse_args(argv)
 
@@ -269,7 +269,7 @@ def roofline_object(ctx, key, flops_per_gpu, kern_s, hbm_bytes):
     return r
 
 
-def measure(ctx, name, steps, warmup, batch=None, e2e=True, parity=True, presoak=None, clocks=False, cpu=False, key=None):
+def measure(ctx, name, steps, warmup, batch=None, e2e=True, parity=True, presoak=None, clocks=False, cpu=False, key=None, strict=None):
     """One workload on this process's GPU (all ranks call it together).  Returns the fields of a bench line."""
     import torch
     from irm_motion_planning_b200 import backend
@@ -283,7 +283,8 @@ def measure(ctx, name, steps, warmup, batch=None, e2e=True, parity=True, presoak
     strong = bool(wl.n_problems)
     wl.args.whole_arm_cost = bool(a.whole_arm)
     joints = 3 if a.whole_arm else 1
-    traj = Trajectory(wl.args, strict_math=a.strict_math)
+    strict = a.strict_math if strict is None else strict
+    traj = Trajectory(wl.args, strict_math=strict)
     traj.set_obstacles(wl.obstacles)
     r_lo, r_hi = 0, wl.n_restarts
     if strong:                                     # every rank: all problems, its block of the restart axis
@@ -470,7 +471,7 @@ def measure(ctx, name, steps, warmup, batch=None, e2e=True, parity=True, presoak
         out.update({
             "value": value, "ms_per_step": 1e3 * total_s / steps, "scaling": "strong" if strong else "weak",
             "config": config_dict(wl, T, world), "launch": h.launch_geometry(B),
-            "math": "strict" if a.strict_math else "fast (rcp.approx)",
+            "math": "strict (IEEE reciprocal, division, square root: bit-exact against the oracle)" if strict else "fast (rcp.approx)",
             "fgd_iters_per_s": n_iter_all * steps / total_s, "mean_inner_iters": float(inner.mean()),
             "fulfilled_frac": float(is_[:, backend.I_FULFILLED].mean()),
             "wall_ms_per_step": 1e3 * (wall1 - wall0) / steps, "step_ms": [round(m, 4) for m in step_ms],
@@ -484,7 +485,7 @@ def measure(ctx, name, steps, warmup, batch=None, e2e=True, parity=True, presoak
             out["dynamic_obstacles"] = {"mode": "live: one persistent launch, the host publishes obstacle sets with fgd_set_obstacles_async "
                                                 "while it runs, every team polls the generation counter every 8 inner iterations" if live
                                         else "one launch per 8 inner iterations", "sets_published_per_step": info["swaps"] / max(steps, 1)}
-        if parity and not a.strict_math:
+        if parity and not strict:
             out["parity"] = parity_check(ctx, wl, traj, alpha0, start, goal, last, last_buf, P, R_local, r_lo)
         if cpu:
             out["cpu_baseline"], _, _ = cpu_baseline(wl, traj, alpha0, start, goal, a.cpu_seconds)
@@ -562,7 +563,11 @@ def main(argv=None):
         plan = {"c2": dict(name="c2", steps=10, warmup=3, e2e=True, presoak=0.2),
                 "c2sat": dict(name="c2", steps=3, warmup=1, batch=65536, e2e=False, presoak=0.0, parity=False, key="c2_b65536"),
                 "c3": dict(name="c3", steps=2, warmup=1, e2e=False, presoak=0.0),
-                "c4": dict(name="c4", steps=2, warmup=1, e2e=False, presoak=0.0, parity=False)}
+                "c4": dict(name="c4", steps=2, warmup=1, e2e=False, presoak=0.0, parity=False),
+                # the reference's own problem (one trajectory): ms_per_step = latency of one optimize() call
+                "c1": dict(name="c1", steps=20, warmup=5, e2e=False, presoak=0.0, parity=False),
+                # the primary workload in strict-math mode: what the bit-exact kernels cost
+                "c5_strict": dict(name="c5", steps=3, warmup=1, e2e=False, presoak=0.0, parity=False, strict=True)}
         for k in [s for s in a.secondary.split(",") if s]:
             r = measure(ctx, **plan[k])
             r.pop("rank", None)

@@ -70,6 +70,12 @@ template <int WPT, bool STRICT, int KS, int NW, int MINB, bool ARM, int TC>
 cudaError_t launch_opt(const DevParams &p, int grid, size_t smem, cudaStream_t st)
 {
     auto kern = p.mode == 0 ? fgd_optimize_kernel<WPT, STRICT, KS, NW, MINB, ARM, TC, 0> : fgd_optimize_kernel<WPT, STRICT, KS, NW, MINB, ARM, TC, 1>;
+    if constexpr (WPT == 1 && KS == K_TMEM && !ARM) {
+        // many obstacles: the instance whose sample-less lanes take a share of the obstacle loop (same bits, same launch bounds)
+        if (share_split(p.T, p.n_obs, false) > 0)
+            kern = p.mode == 0 ? fgd_optimize_kernel<WPT, STRICT, KS, NW, MINB, ARM, TC, 0, 0, false, true>
+                               : fgd_optimize_kernel<WPT, STRICT, KS, NW, MINB, ARM, TC, 1, 0, false, true>;
+    }
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, NW * 32, smem, st>>>(p);

@@ -853,9 +853,10 @@ __device__ __forceinline__ void obstacle_range(const float2 *__restrict__ sObs, 
 // The obstacle loop accumulates sum 1/(2 den) and sum d/(2 den)^2; the constant factors
 // 0.8 and -0.8 of environment.py:43,57 (times 2 and 4) are applied once per sample.
 // ---------------------------------------------------------------------------
-// split: share_split() of this launch / obstacle set (0: one chain per sample); HELP: the tail chain runs on the helper
-// lanes, XA / XB = the team's operand buffers as scratch.
-template <int WPT, bool STRICT, bool ARM, bool PIPE = false, bool OPAQUE_POS = false, bool HELP = false>
+// split: share_split() of this launch / obstacle set (0: one chain per sample).  SHARE = 2: the tail chain runs on the
+// helper lanes, XA / XB = the team's operand buffers as scratch; 1: both chains in the owner lane; 0: the caller guarantees
+// split == 0 (the host launches the helper instance for every scene with an active split) and the code is left out.
+template <int WPT, bool STRICT, bool ARM, bool PIPE = false, bool OPAQUE_POS = false, int SHARE = 1>
 __device__ __forceinline__ void cost_phase(const DevParams &p, const int T, const float2 *__restrict__ sObs, const int n_obs, const Team<WPT> &G,
                                            const f2 (&yq)[3], const f2 (&yv)[3],
                                            const float *start, const float *goal, float lam_sg, float lam_jl,
@@ -917,8 +918,8 @@ __device__ __forceinline__ void cost_phase(const DevParams &p, const int T, cons
 #pragma unroll
     for (int j = 0; j < NJ; ++j) { sr[j] = bc2(0.0f); sx[j] = bc2(0.0f); sy[j] = bc2(0.0f); }
     int o = 0;
-    if (!ARM && WPT == 1 && split > 0) {                   // warp-uniform: two chains per sample (see share_split)
-        if constexpr (!ARM && WPT == 1 && HELP) {
+    if (SHARE > 0 && !ARM && WPT == 1 && split > 0) {      // warp-uniform: two chains per sample (see share_split)
+        if constexpr (!ARM && WPT == 1 && SHARE == 2) {
             const int n_act = (T + 1) >> 1, n_help = 32 - n_act, k = (n_act + n_help - 1) / n_help, lseg = split / k;
             const bool helper = G.lane >= n_act;
             if (!helper) XA[G.lane] = make_float4(px[2].x, px[2].y, py[2].x, py[2].y);

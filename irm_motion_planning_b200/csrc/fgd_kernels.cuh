@@ -355,10 +355,13 @@ __device__ __forceinline__ void log_switch(const DevParams &p, const int lane, c
 // the iterates are the reference's bit for bit.  Gradient trips are computed redundantly by all replicas from the
 // winner's operand buffer.
 // LIVE: live obstacle updates (fgd_optimize_live): a private obstacle set per team, polled and refreshed in the kernel.
-template <int WPT, bool STRICT, int KS, int NW, int MINB, bool ARM, int TC, int MODE, int SPEC = 0, bool LIVE = false>
+// HELP: the obstacle loop of a many-obstacle scene is shared with the warp's sample-less lanes (fgd_device.cuh, share_split);
+// the host launches this instance when the split is active, the LIVE instances always carry it.
+template <int WPT, bool STRICT, int KS, int NW, int MINB, bool ARM, int TC, int MODE, int SPEC = 0, bool LIVE = false, bool HELP = LIVE>
 __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __grid_constant__ DevParams p)
 {
     constexpr bool SP = SPEC > 0;
+    static_assert(!HELP || (WPT == 1 && !ARM && !SP), "helper lanes: single-warp teams, end-effector cost");
     static_assert(!LIVE || (WPT == 1 && !SP), "live obstacle updates: single-warp teams");
     static_assert(!SP || (WPT == 1 && MODE == 0 && NW == SPEC && SPEC <= 8), "speculative line search: BLS, single-warp replicas, one trajectory per CTA");
     static_assert(TC == 0 || KS == K_TMEM, "compile-time T: TMEM instances only");
@@ -391,7 +394,13 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
     (void)kd; (void)ko; (void)dd; (void)tk;
     int n_obs_live = 0, cur_gen = -1, polled_at = -1, n_switch = 0;       // LIVE: the team's obstacle set and poll bookkeeping
     (void)n_obs_live; (void)cur_gen; (void)polled_at; (void)n_switch;
-    int split = LIVE ? 0 : share_split(T, p.n_obs, ARM);                  // two-chain obstacle sums (fgd_device.cuh, share_split); LIVE: follows the adopted set
+    // two-chain obstacle sums (fgd_device.cuh, share_split): 2 = on the helper lanes, 1 = both chains in the owner lane, 0 = never
+    // active here (the default single-warp-team instance: the host launches its HELP twin for every scene with an active split)
+    constexpr int SHARE = HELP ? 2 : ((WPT == 1 && KS == K_TMEM && !ARM && !SP && !LIVE) ? 0 : 1);
+    int split = (LIVE || SHARE == 0) ? 0 : share_split(T, p.n_obs, ARM);  // LIVE: follows the adopted obstacle set
+    if constexpr (SHARE == 0) {
+        if (share_split(T, p.n_obs, ARM) > 0) __trap();                    // launched for a scene that needs the HELP twin: a host-side dispatch bug
+    }
     __shared__ SpecScratch sp_mem;                                          // SPEC only (a few words)
     SpecScratch *sp = &sp_mem;
     const int rep = SP ? (int)(threadIdx.x >> 5) : 0;                       // replica index = candidate offset in a round
@@ -485,7 +494,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
             Rows<ARM> Rw;
             float loss_c, toc_c;
             int ful_c;
-            cost_phase<WPT, STRICT, ARM, (WPT > 1), LIVE, LIVE>(p, T, sObs, LIVE ? n_obs_live : p.n_obs, G, y1, y2, st.start, st.goal, st.lam_sg, st.lam_jl, Rw, loss_c, toc_c, ful_c,
+            cost_phase<WPT, STRICT, ARM, (WPT > 1), LIVE, SHARE>(p, T, sObs, LIVE ? n_obs_live : p.n_obs, G, y1, y2, st.start, st.goal, st.lam_sg, st.lam_jl, Rw, loss_c, toc_c, ful_c,
                                                                 split, XA, XB);
             PCLK(1);
             bool accept = false;

@@ -14,4 +14,4 @@ python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches_default.csv \
   python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-parity --no-secondary > gpurun_out/${TAG}_launches_default.log 2>&1
 echo "launch list rc=$?"
-bash profiles/scripts/r02_counters.sh ${TAG} c3:4096:full c5:65536:full
+bash profiles/scripts/r02_counters.sh ${TAG} c3:4096:full c5:65536:full c2:65536:full c4:32768:full

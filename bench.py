@@ -261,8 +261,9 @@ def roofline_object(ctx, key, flops_per_gpu, kern_s, hbm_bytes):
     if ex.get("fp32_flop_per_alg_flop"):
         r["executed_frac"] = r["frac"] * ex["fp32_flop_per_alg_flop"] if r["frac"] is not None else None
         r["executed"] = {"fp32_flop_per_algorithmic_flop": ex["fp32_flop_per_alg_flop"], "source": ex.get("source"),
-                         "note": "executed FFMA/FADD/FMUL thread instructions (ncu smsp__sass_thread_inst_executed_op_f*_pred_on, FMA = 2) "
-                                 "per algorithmic FLOP of the same launch; < 1 because q, v and the loss of an accepted candidate are reused"}
+                         "note": "executed FP32 flops (SASS opcode histogram of the ncu --set full source page, warp level: FFMA2 = 128, "
+                                 "FADD2 / FMUL2 / FFMA = 64, FADD / FMUL = 32 per warp instruction) per algorithmic FLOP of the same launch; "
+                                 "< 1 because q, v and the loss of an accepted candidate are reused and the sparse dK product skips zeros"}
     if ex.get("mufu_per_alg_flop") and ctx.peak_mufu:
         r["mufu_frac"] = ex["mufu_per_alg_flop"] * flops_per_gpu / kern_s * 1e-12 / ctx.peak_mufu
         r["mufu_peak_trcp"] = ctx.peak_mufu

@@ -19,7 +19,7 @@ python - <<PY
 import json
 for n in ("c5","c2"):
     try:
-        d=json.load(open("gpurun_out/${TAG}_%s_n$N.json" % n)); print(n, "N=$N", d["value"], "ms", d["ms_per_step"], "frac", d["roofline"]["frac"], "e2e", d["e2e"]["value"], d.get("sweep"))
+        d=json.loads([l for l in open("gpurun_out/${TAG}_%s_n$N.json" % n) if l.startswith("{")][-1]); print(n, "N=$N", d["value"], "ms", d["ms_per_step"], "frac", d["roofline"]["frac"], "e2e", d["e2e"]["value"], d.get("sweep"))
     except Exception as e: print(n, "failed", e)
 PY
 cat gpurun_out/${TAG}_nccl_n$N.txt

@@ -34,7 +34,12 @@
  *   - alpha_norm = sum_t (sum_a g[t,a]) * (sum_b n[t,b]), algebraically equal
  *     to sum(g.T @ n)                              (optimizer_BLS.py:166)
  *   - sin/cos: Cody-Waite reduction + cephes minimax polynomials written out
- *     below (<= 2 ulp), instead of the platform libm.
+ *     below (<= 2 ulp), instead of the platform libm; the quadrant comes from a
+ *     magic-number rounding fma(x, 2/pi, 1.5 * 2^23) (round to nearest even).
+ *   - trajectories of T <= 64 samples facing >= 64 obstacles sum the potential of a
+ *     sample as TWO chains, [0, S) and [S, n_obs) (share_split(): the CUDA side runs
+ *     the second chain on the lanes of the warp that own no sample); checked against
+ *     the FP64 NumPy oracle in tests/test_oracle_mirror.py.
  *
  * Extension (cfg.whole_arm, not in the reference's code; its blog, DevBlog-Theme/
  * blog-post.html:505-513, names it): cost_v[t] = sum_j costmap(fk_j(q_t)) over the three

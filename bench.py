@@ -568,7 +568,7 @@ def main(argv=None):
                 # the reference's own problem (one trajectory): ms_per_step = latency of one optimize() call
                 "c1": dict(name="c1", steps=20, warmup=5, e2e=False, presoak=0.0, parity=False),
                 # the primary workload in strict-math mode: what the bit-exact kernels cost
-                "c5_strict": dict(name="c5", steps=3, warmup=1, e2e=False, presoak=0.0, parity=False, strict=True)}
+                "c5_strict": dict(name="c5", steps=3, warmup=1, e2e=False, presoak=0.0, parity=False, strict=True, key="c5_strict")}
         for k in [s for s in a.secondary.split(",") if s]:
             r = measure(ctx, **plan[k])
             r.pop("rank", None)

@@ -53,7 +53,7 @@ run(100, 20, "bls", n_obs=40, **small)           # two-warp teams, K and dK in T
 run(256, 10, "bls", n_obs=130, **small)          # four-warp teams, K in TMEM, dK from L2, pipelined obstacle loop
 run(200, 9, "gd", n_obs=33, **small)
 run(50, 300, "bls", n_obs=70, live=True, max_inner_iteration=8, max_outer_iteration=2)      # LIVE: helper lanes share the obstacle loop
-run(50, 200, "bls", n_obs=300, **small)          # static many-obstacle scene: the HELP twin instance
+run(50, 600, "bls", n_obs=300, **small)          # static many-obstacle scene, batch above the speculative limit: the HELP twin instance
 run(33, 60, "gd", n_obs=100, **small)
 tr, eng, a0, start, goal = run(50, 8, "gd", **small)
 res = eng.optimize_host(a0, start, goal)         # staged host path

@@ -816,9 +816,11 @@ __device__ __forceinline__ void obstacle_pair_tail(const ObsPair &P, f2 &sr, f2 
 // lane sums the obstacles [0, S), a helper lane sums the tail [S, n_obs) of up to k = ceil(n_act / n_help) owners one
 // after the other (positions and partial sums travel through the team's operand buffers, which are idle during the cost
 // phase), and the owner adds the helper's partial to its own: sr = srA + srB, sx = sxA + sxB, sy = syA + syB - each chain
-// in ascending obstacle order from zero.  S = k * Lseg with Lseg = 4 * ceil(n_obs / (4 (k + 1))), so that k owner
-// segments and one tail are equally long: T = 50, 256 obstacles: k = 4, S = 208, tail 48 - 208 loop steps per lane
-// instead of 256.  The split is part of the documented summation order (the mirror oracle follows it) whenever
+// from zero.  S = k * Lseg with Lseg = 4 * ceil(n_obs / (4 (k + 1))), so that k owner segments and one tail are equally
+// long: T = 50, 256 obstacles: k = 4, S = 208, tail 48 - 208 loop steps per lane instead of 256.  The helper chain is whole
+// blocks of four: the last rem = (n_obs - S) mod 4 obstacles belong to the OWNER's chain, after its [0, S) (one piece of
+// remainder code per evaluation instead of one per helper segment):
+//     chain A = [0, S) ++ [n_obs - rem, n_obs),   chain B = [S, n_obs - rem),   each ascending.  The split is part of the documented summation order (the mirror oracle follows it) whenever
 // share_split() > 0: single-warp teams, end-effector cost, at least FGD_SHARE_MIN_OBS obstacles.  Instances without the
 // helper code (HELP = false) evaluate both chains in the owner lane - same bits.
 // ---------------------------------------------------------------------------
@@ -834,14 +836,19 @@ __host__ __device__ inline int share_split(int T, int n_obs, bool whole_arm)
     return S < n_obs ? S : 0;
 }
 
-// obstacles [o0, o1) against the row pair at (x, y), ascending, block form (o0 even)
+// obstacles [o0, o1) against the row pair at (x, y), ascending, in blocks of four (o0 and o1 - o0 multiples of four)
 template <bool STRICT>
-__device__ __forceinline__ void obstacle_range(const float2 *__restrict__ sObs, int o0, const int o1, const f2 x, const f2 y, f2 &sr, f2 &sx, f2 &sy)
+__device__ __forceinline__ void obstacle_range4(const float2 *__restrict__ sObs, int o0, const int o1, const f2 x, const f2 y, f2 &sr, f2 &sx, f2 &sy)
 {
 #pragma unroll 1
-    for (; o0 + 4 <= o1; o0 += 4) obstacle_block<4, STRICT>(sObs + o0, x, y, sr, sx, sy);
-    if (o0 + 2 <= o1) { obstacle_block<2, STRICT>(sObs + o0, x, y, sr, sx, sy); o0 += 2; }
-    if (o0 < o1) obstacle_block<1, STRICT>(sObs + o0, x, y, sr, sx, sy);
+    for (; o0 < o1; o0 += 4) obstacle_block<4, STRICT>(sObs + o0, x, y, sr, sx, sy);
+}
+// the last obstacles [o0, n_obs) one at a time (any alignment; at most three)
+template <bool STRICT>
+__device__ __forceinline__ void obstacle_singles(const float2 *__restrict__ sObs, int o0, const int n_obs, const f2 x, const f2 y, f2 &sr, f2 &sx, f2 &sy)
+{
+#pragma unroll 1
+    for (; o0 < n_obs; ++o0) obstacle_block<1, STRICT>(sObs + o0, x, y, sr, sx, sy);
 }
 
 // ---------------------------------------------------------------------------
@@ -921,6 +928,7 @@ __device__ __forceinline__ void cost_phase(const DevParams &p, const int T, cons
     if (SHARE > 0 && !ARM && WPT == 1 && split > 0) {      // warp-uniform: two chains per sample (see share_split)
         if constexpr (!ARM && WPT == 1 && SHARE == 2) {
             const int n_act = (T + 1) >> 1, n_help = 32 - n_act, k = (n_act + n_help - 1) / n_help, lseg = split / k;
+            const int tail_end = n_obs - ((n_obs - split) & 3);
             const bool helper = G.lane >= n_act;
             if (!helper) XA[G.lane] = make_float4(px[2].x, px[2].y, py[2].x, py[2].y);
             __syncwarp();
@@ -933,14 +941,15 @@ __device__ __forceinline__ void cost_phase(const DevParams &p, const int T, cons
                     const float4 pq = XA[own < n_act ? own : 0];
                     x = mk2(pq.x, pq.y); y = mk2(pq.z, pq.w);
                     sr[0] = bc2(0.0f); sx[0] = bc2(0.0f); sy[0] = bc2(0.0f);
-                    o0 = split; o1 = own < n_act ? n_obs : split;
+                    o0 = split; o1 = own < n_act ? tail_end : split;
                 }
-                obstacle_range<STRICT>(sObs, o0, o1, x, y, sr[0], sx[0], sy[0]);
+                obstacle_range4<STRICT>(sObs, o0, o1, x, y, sr[0], sx[0], sy[0]);
                 if (helper && own < n_act) {
                     XA[own] = make_float4(sr[0].x, sr[0].y, sx[0].x, sx[0].y);
                     XB[own] = make_float4(sy[0].x, sy[0].y, 0.0f, 0.0f);
                 }
             }
+            obstacle_singles<STRICT>(sObs, tail_end, n_obs, px[2], py[2], sr[0], sx[0], sy[0]);      // the owners' chain ends with the remainder
             __syncwarp();
             if (!helper) {
                 const float4 r0 = XA[G.lane], r1 = XB[G.lane];
@@ -949,8 +958,10 @@ __device__ __forceinline__ void cost_phase(const DevParams &p, const int T, cons
             __syncwarp();                                  // the scratch rows are free again
         } else {
             f2 tr = bc2(0.0f), tx = bc2(0.0f), ty = bc2(0.0f);
-            obstacle_range<STRICT>(sObs, 0, split, px[2], py[2], sr[0], sx[0], sy[0]);
-            obstacle_range<STRICT>(sObs, split, n_obs, px[2], py[2], tr, tx, ty);
+            const int tail_end = n_obs - ((n_obs - split) & 3);
+            obstacle_range4<STRICT>(sObs, 0, split, px[2], py[2], sr[0], sx[0], sy[0]);
+            obstacle_singles<STRICT>(sObs, tail_end, n_obs, px[2], py[2], sr[0], sx[0], sy[0]);
+            obstacle_range4<STRICT>(sObs, split, tail_end, px[2], py[2], tr, tx, ty);
             sr[0] = add2(sr[0], tr); sx[0] = add2(sx[0], tx); sy[0] = add2(sy[0], ty);
         }
         o = n_obs;

@@ -37,9 +37,9 @@
  *     below (<= 2 ulp), instead of the platform libm; the quadrant comes from a
  *     magic-number rounding fma(x, 2/pi, 1.5 * 2^23) (round to nearest even).
  *   - trajectories of T <= 64 samples facing >= 64 obstacles sum the potential of a
- *     sample as TWO chains, [0, S) and [S, n_obs) (share_split(): the CUDA side runs
- *     the second chain on the lanes of the warp that own no sample); checked against
- *     the FP64 NumPy oracle in tests/test_oracle_mirror.py.
+ *     sample as TWO chains (share_split(): the CUDA side runs the second chain, whole
+ *     blocks of four obstacles, on the lanes of the warp that own no sample); checked
+ *     against the FP64 NumPy oracle in tests/test_oracle_mirror.py.
  *
  * Extension (cfg.whole_arm, not in the reference's code; its blog, DevBlog-Theme/
  * blog-post.html:505-513, names it): cost_v[t] = sum_j costmap(fk_j(q_t)) over the three
@@ -133,9 +133,10 @@ static void mirror_sincos(float x, float *s_out, float *c_out)
  * CUDA side (csrc/fgd_device.cuh).                                                         */
 static int warps_per_trajectory(int T) { return T <= 64 ? 1 : (T <= 128 ? 2 : (T <= 256 ? 4 : 8)); }
 
-/* Obstacle sums of single-warp teams with many obstacles are TWO chains per sample, [0, S) and [S, n_obs), each in
- * ascending order from zero, added at the end (csrc/fgd_device.cuh, share_split: the tail chain runs on the lanes of the
- * warp that own no sample).  0 = one chain. */
+/* Obstacle sums of single-warp teams with many obstacles are TWO chains per sample, each from zero, added at the end
+ * (csrc/fgd_device.cuh, share_split: chain B runs on the lanes of the warp that own no sample, in whole blocks of four):
+ *     chain A = [0, S) ++ [n_obs - rem, n_obs),  chain B = [S, n_obs - rem),  rem = (n_obs - S) mod 4,  each ascending.
+ * share_split() returns S; 0 = one chain. */
 static int share_split(int T, int n_obs, int whole_arm)
 {
     if (T > 64 || whole_arm || n_obs < 64) return 0;
@@ -224,20 +225,25 @@ static void evaluate_point(const MirrorCfg *c, const Derived *d, const float *K,
         px[0] = c->link[0] * cs[t][0]; px[1] = fmaf(c->link[1], cs[t][1], px[0]); px[2] = fmaf(c->link[2], cs[t][2], px[1]);
         py[0] = c->link[0] * sn[t][0]; py[1] = fmaf(c->link[1], sn[t][1], py[0]); py[2] = fmaf(c->link[2], sn[t][2], py[1]);
         const int split = share_split(T, c->n_obs, c->whole_arm);
+        const int tail_end = split > 0 ? c->n_obs - ((c->n_obs - split) & 3) : c->n_obs;
         for (int j = j_lo; j < 3; ++j) {
-            float sr = 0.0f, sx = 0.0f, sy = 0.0f;
-            float hr = 0.0f, hx = 0.0f, hy = 0.0f;           /* the chain before the split point */
-            for (int o = 0; o < c->n_obs; ++o) {             /* environment.py:46-58 */
-                if (split > 0 && o == split) { hr = sr; hx = sx; hy = sy; sr = 0.0f; sx = 0.0f; sy = 0.0f; }
-                float dx = px[j] - obs[2 * o], dy = py[j] - obs[2 * o + 1];
-                float m = fmaf(dy, dy, fmaf(dx, dx, 1.0f));  /* 2 den = 1 + |f-o|^2  */
-                float r = 1.0f / m;
-                sr = sr + r;                                 /* sum 1/(2 den)        */
-                float r2 = r * r;
-                sx = fmaf(r2, dx, sx);                       /* sum d/(2 den)^2      */
-                sy = fmaf(r2, dy, sy);
+            float acc[2][3] = { { 0.0f, 0.0f, 0.0f }, { 0.0f, 0.0f, 0.0f } };   /* chain A, chain B: sr, sx, sy */
+            for (int pass = 0; pass < (split > 0 ? 2 : 1); ++pass) {
+                for (int o = 0; o < c->n_obs; ++o) {         /* environment.py:46-58 */
+                    const int in_b = split > 0 && o >= split && o < tail_end;
+                    if (in_b != pass) continue;              /* pass 0: chain A (ascending, the remainder last), pass 1: chain B */
+                    float *a = acc[pass];
+                    float dx = px[j] - obs[2 * o], dy = py[j] - obs[2 * o + 1];
+                    float m = fmaf(dy, dy, fmaf(dx, dx, 1.0f));  /* 2 den = 1 + |f-o|^2  */
+                    float r = 1.0f / m;
+                    a[0] = a[0] + r;                         /* sum 1/(2 den)        */
+                    float r2 = r * r;
+                    a[1] = fmaf(r2, dx, a[1]);               /* sum d/(2 den)^2      */
+                    a[2] = fmaf(r2, dy, a[2]);
+                }
             }
-            if (split > 0) { sr = hr + sr; sx = hx + sx; sy = hy + sy; }
+            float sr = acc[0][0], sx = acc[0][1], sy = acc[0][2];
+            if (split > 0) { sr = sr + acc[1][0]; sx = sx + acc[1][1]; sy = sy + acc[1][2]; }
             srj[j] = sr; cj[j] = 1.6f * sr; gx[t][j] = -3.2f * sx; gy[t][j] = -3.2f * sy;
         }
         /* whole arm: c_1 + c_2 + c_3 as fma(1.6, s_3, fma(1.6, s_2, 1.6 * s_1)) */

@@ -55,6 +55,9 @@ def parse(argv=None):
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary workloads of the default single-GPU run")
     ap.add_argument("--secondary", default="c2,c2sat,c3,c4,c1,c5_strict", help="secondary workloads of the default single-GPU run")
     ap.add_argument("--c4-relaunch", action="store_true", help="c4 through one launch per 8 iterations (round-1 path) instead of the live kernel")
+    ap.add_argument("--c4-max-sets", type=int, default=-1,
+                    help="c4 live: publish at most N obstacle sets per launch (-1 = until the launch ends; 0 = a deterministic launch for ncu "
+                         "captures: under kernel replay the publisher's timing differs from pass to pass)")
     return ap.parse_args(argv)
 
 
@@ -315,7 +318,8 @@ def measure(ctx, name, steps, warmup, batch=None, e2e=True, parity=True, presoak
         fs, is_ = eng.new_state(B)
         keys = None
         if name == "c4" and live:
-            info["swaps"] += eng.optimize_live(buf, s_dev, g_dev, fs, is_, swaps, poll_every=8)
+            info["swaps"] += eng.optimize_live(buf, s_dev, g_dev, fs, is_, swaps, poll_every=8,
+                                               max_sets=None if a.c4_max_sets < 0 else a.c4_max_sets)
         elif name == "c4":
             for k in range(10000):
                 h.set_obstacles(swaps[k % len(swaps)])

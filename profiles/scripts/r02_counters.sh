@@ -7,6 +7,8 @@ M=smsp__sass_thread_inst_executed_op_ffma_pred_on.sum,smsp__sass_thread_inst_exe
 run() {
   W=$1; B=$2; FULL=$3
   ARGS="--workload $W --batch $B --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-parity --no-secondary --presoak-seconds 0"
+  # config 4 (live obstacle updates): a launch without updates, so that every replay pass of ncu sees the same work
+  [ "$W" = "c4" ] && ARGS="$ARGS --c4-max-sets 0"
   N=${TAG}_${W}_b${B}
   timeout 600 python bench.py $ARGS > gpurun_out/${N}_plain.json 2> gpurun_out/${N}_plain.err || { echo "$N plain run failed"; tail -3 gpurun_out/${N}_plain.err; return 1; }
   timeout 900 ncu --metrics $M --clock-control none -k regex:fgd_optimize_kernel -s 1 -c 1 --csv --log-file gpurun_out/${N}_counters.csv python bench.py $ARGS > gpurun_out/${N}_counters.json 2> gpurun_out/${N}_counters.err

@@ -3,23 +3,26 @@
 // Mapping.  A trajectory is owned by a TEAM of WPT warps
 // (WPT = 1 for T <= 64, 2 for T <= 128, 4 for T <= 256).  Team thread i
 // (i = 32 * warp_in_team + lane) owns the R = 2 adjacent time samples t = 2i, 2i+1,
-// handled as ONE packed FP32 row pair.  The RKHS contraction produces rows t of
-// q = K alpha J and v = dK alpha J in the thread that then does forward
-// kinematics, the obstacle potential and the penalty terms for those samples --
-// no shared-memory round trip between the two.  K and dK are re-laid out per
-// column k so that a thread fetches its entries of column k with one 128-bit
-// load: from shared memory (staged once per CTA) for T <= 64, from L2 through the
-// read-only path for larger T.  The operand rows (alpha' or the q/v-gradients) sit
-// in a per-team shared buffer and enter the FFMA2 as broadcast scalars.
-// Reductions over t: lane-serial over the 2 rows, a 5-step xor butterfly inside
-// each warp, then -- WPT > 1 -- the warp partials are exchanged through shared
-// memory and combined as (p0 + p1) + (p2 + p3): the order the mirror oracle
-// reproduces.  All trajectory-level decisions are computed redundantly by every
-// thread of the team from the same reduced values, so the team stays convergent
-// (team barrier = __syncwarp for WPT = 1, the CTA barrier for WPT > 1: a CTA is
-// exactly one team then).
+// handled as ONE packed FP32 row pair (FFMA2 / FADD2 / FMUL2).  The RKHS contraction
+// produces rows t of q = K alpha J and v = dK alpha J in the thread that then does
+// forward kinematics, the obstacle potential and the penalty terms for those samples --
+// no shared-memory round trip between the two.  K and dK are re-laid out per column k so
+// that a thread fetches its entries of column k with one access: from TENSOR MEMORY
+// (tcgen05.ld, the default: one table copy per SM shared by all its teams), from shared
+// memory or from L2 (the A/B variants and the evaluation kernel).  The operand rows
+// (alpha' or the q/v-gradients) sit in a per-team shared buffer and enter the FFMA2 as
+// broadcast scalars.
+// Reductions over t: lane-serial over the 2 rows, a 5-step xor butterfly inside each
+// warp (three sums share one transposed butterfly, the maximum is one integer REDUX),
+// then -- WPT > 1 -- the warp partials are exchanged through shared memory and combined
+// as (p0 + p1) + (p2 + p3): the order the mirror oracle reproduces.  All trajectory-level
+// decisions are computed redundantly by every thread of the team from the same reduced
+// values, so the team stays convergent (team barrier = __syncwarp for WPT = 1, a named
+// barrier per team for WPT > 1, the CTA barrier when a team owns its CTA).
+// Lanes of a single-warp team that own no sample (T = 50: 7 of 32) take a share of the
+// obstacle loop in many-obstacle scenes (share_split, cost_phase).
 //
-// Compiled with -fmad=false: every fused multiply-add is an explicit fmaf(), so
+// Compiled with -fmad=false: every fused multiply-add is an explicit fmaf() / fma2(), so
 // the operation sequence is the documented one (bit-exact against the oracle in
 // strict-math mode).
 #pragma once

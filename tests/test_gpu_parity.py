@@ -76,6 +76,27 @@ def test_eval_bit_exact_strict(cuda_ready, T, n_obs):
             assert np.array_equal(g["fulfilled"], c["fulfilled"])
 
 
+@pytest.mark.parametrize("T,n_obs", [(50, 13), (50, 80), (256, 20)])
+def test_strict_reciprocal_slow_path_far_obstacles(cuda_ready, T, n_obs):
+    """rcp_block (csrc/fgd_device.cuh): strict mode takes the packed Newton step only while every m = 1 + |f - o|^2 of a
+    block is below 2^126; a block with an absurdly distant obstacle goes through __frcp_rn (denormal reciprocals, m = inf).
+    Obstacles at 1e19 (m ~ 1e38 >= 2^126, 1/m denormal) and 1e20 (m overflows to inf, 1/m = 0) among ordinary ones:
+    still bit-identical to the oracle's IEEE 1 / m, per evaluation and over a short optimisation."""
+    args, tr, obs, start, goal, alpha0 = _setup(T=T, n_obs=n_obs, B=24, seed=3, max_inner_iteration=10, max_outer_iteration=2)
+    obs = np.array(obs, np.float32).copy()
+    obs[1] = (1e19, -2.0); obs[n_obs // 2] = (0.5, -1e20); obs[-1] = (-1e19, 1e19); obs[5] = (3e18, 4e18)
+    tr.set_obstacles(obs)
+    m = _mirror(args, tr, obs, "bls")
+    for lam in ((0.5, 0.1), (500.0, 100.0)):
+        g = _gpu_eval(tr, alpha0, start, goal, *lam)
+        c = m.eval(alpha0, start, goal, *lam)
+        for k in ("loss", "toc", "grad"):
+            assert np.array_equal(g[k], c[k]), (T, n_obs, lam, k)
+    a, fs, is_ = _gpu_optimize(tr, "bls", alpha0, start, goal)
+    ca, cfs, cis = m.optimize(alpha0, start, goal)
+    assert np.array_equal(is_.cpu().numpy(), cis) and np.array_equal(a.cpu().numpy(), ca)
+
+
 def test_eval_fast_math_within_tolerance(cuda_ready, oracle_vectors):
     """Fast mode vs the committed NumPy-oracle vectors (FP64): loss rel <= 1e-5, grad rel <= 1e-5."""
     args, tr, obs, *_ = _setup(strict=False, B=1)

@@ -611,13 +611,15 @@ def test_two_streams_on_one_handle(cuda_ready):
             assert torch.equal(ins[i][0], ref[i][0]) and torch.equal(ins[i][4], ref[i][2])
 
 
-@pytest.mark.parametrize("mode,strict", [("bls", True), ("gd", True), ("bls", False)])
-def test_live_obstacle_updates_replay_bit_exact(cuda_ready, mode, strict):
+@pytest.mark.parametrize("mode,strict,lo", [("bls", True, 192), ("gd", True, 192), ("bls", False, 192), ("bls", True, 20)])
+def test_live_obstacle_updates_replay_bit_exact(cuda_ready, mode, strict, lo):
     """Config 4 without relaunches (fgd_optimize_live): ONE persistent launch while the host publishes new obstacle sets
     (count changes too) with fgd_set_obstacles_async on a side stream; every team polls the generation counter every 4
     inner iterations of its trajectory.  Which generation a trajectory saw at which iteration depends on timing, so the
     kernel records it (switch log) and the oracle REPLAYS that schedule per trajectory through its budgeted entry - the
     plain loop's semantics (optimizer_BLS.py:79,82,90): bit-identical alpha, counters and loss state (strict mode).
+    The sets have 192-320 obstacles (20-320 in the last case), so the helper lanes of the shared obstacle loop are at work
+    and, in the last case, switch on and off with the adopted set.
     Fast mode: the same replay through the budgeted CUDA entry points (relaunch path) gives identical bits."""
     import torch
     from irm_motion_planning_b200 import backend
@@ -626,7 +628,8 @@ def test_live_obstacle_updates_replay_bit_exact(cuda_ready, mode, strict):
     B, POLL = 600, 4
     over = {} if mode == "bls" else {"max_outer_iteration": 3}
     args, tr, obs, start, goal, alpha0 = _setup(B=B, n_obs=256, seed=17, strict=strict, **over)
-    sets = [np.asarray(obs, np.float32)] + [obstacle_swap(k, seed=17) for k in range(1, 40)]
+    # lo = 20: the obstacle count crosses the 64-obstacle threshold of the shared obstacle loop (share_split) from set to set
+    sets = [np.asarray(obs, np.float32)] + [obstacle_swap(k, seed=17, lo=lo) for k in range(1, 40)]
     eng = BatchedFGD(tr, mode)
     a = torch.as_tensor(alpha0, device="cuda").clone()
     s, g = torch.as_tensor(start, device="cuda").contiguous(), torch.as_tensor(goal, device="cuda").contiguous()

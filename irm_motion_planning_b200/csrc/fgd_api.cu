@@ -108,6 +108,8 @@ template <bool STRICT, int TC>
 cudaError_t launch_spec(const DevParams &p, int grid, size_t smem, cudaStream_t st)
 {
     auto kern = fgd_optimize_kernel<1, STRICT, K_TMEM, SPEC_WARPS, 2, false, TC, 0, SPEC_WARPS>;
+    if (share_split(p.T, p.n_obs, false) > 0)          // many obstacles: the replicas' sample-less lanes share the obstacle loop
+        kern = fgd_optimize_kernel<1, STRICT, K_TMEM, SPEC_WARPS, 2, false, TC, 0, SPEC_WARPS, false, true>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, SPEC_WARPS * 32, smem, st>>>(p);

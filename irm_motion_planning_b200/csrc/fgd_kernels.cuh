@@ -361,7 +361,7 @@ template <int WPT, bool STRICT, int KS, int NW, int MINB, bool ARM, int TC, int 
 __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __grid_constant__ DevParams p)
 {
     constexpr bool SP = SPEC > 0;
-    static_assert(!HELP || (WPT == 1 && !ARM && !SP), "helper lanes: single-warp teams, end-effector cost");
+    static_assert(!HELP || (WPT == 1 && !ARM), "helper lanes: single-warp teams, end-effector cost");
     static_assert(!LIVE || (WPT == 1 && !SP), "live obstacle updates: single-warp teams");
     static_assert(!SP || (WPT == 1 && MODE == 0 && NW == SPEC && SPEC <= 8), "speculative line search: BLS, single-warp replicas, one trajectory per CTA");
     static_assert(TC == 0 || KS == K_TMEM, "compile-time T: TMEM instances only");

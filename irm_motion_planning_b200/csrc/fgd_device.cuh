@@ -866,7 +866,9 @@ __device__ __forceinline__ void obstacle_singles(const float2 *__restrict__ sObs
 // split: share_split() of this launch / obstacle set (0: one chain per sample).  SHARE = 2: the tail chain runs on the
 // helper lanes, XA / XB = the team's operand buffers as scratch; 1: both chains in the owner lane; 0: the caller guarantees
 // split == 0 (the host launches the helper instance for every scene with an active split) and the code is left out.
-template <int WPT, bool STRICT, bool ARM, bool PIPE = false, bool OPAQUE_POS = false, int SHARE = 1>
+// OC > 0: the obstacle count is the compile-time constant OC (the reference's default scene has 11): the loop is straight-line
+// code in blocks of 4, 2, 1 - no loop control, and ptxas schedules across the blocks.  Same blocks in the same order.
+template <int WPT, bool STRICT, bool ARM, bool PIPE = false, bool OPAQUE_POS = false, int SHARE = 1, int OC = 0>
 __device__ __forceinline__ void cost_phase(const DevParams &p, const int T, const float2 *__restrict__ sObs, const int n_obs, const Team<WPT> &G,
                                            const f2 (&yq)[3], const f2 (&yv)[3],
                                            const float *start, const float *goal, float lam_sg, float lam_jl,
@@ -928,7 +930,13 @@ __device__ __forceinline__ void cost_phase(const DevParams &p, const int T, cons
 #pragma unroll
     for (int j = 0; j < NJ; ++j) { sr[j] = bc2(0.0f); sx[j] = bc2(0.0f); sy[j] = bc2(0.0f); }
     int o = 0;
-    if (SHARE > 0 && !ARM && WPT == 1 && split > 0) {      // warp-uniform: two chains per sample (see share_split)
+    if constexpr (OC > 0 && !ARM && WPT == 1) {
+#pragma unroll
+        for (int ob = 0; ob + 4 <= OC; ob += 4) obstacle_block<4, STRICT>(sObs + ob, px[2], py[2], sr[0], sx[0], sy[0]);
+        if constexpr ((OC & 3) >= 2) obstacle_block<2, STRICT>(sObs + (OC & ~3), px[2], py[2], sr[0], sx[0], sy[0]);
+        if constexpr (OC & 1) obstacle_block<1, STRICT>(sObs + (OC & ~1), px[2], py[2], sr[0], sx[0], sy[0]);
+        o = n_obs;
+    } else if (SHARE > 0 && !ARM && WPT == 1 && split > 0) {      // warp-uniform: two chains per sample (see share_split)
         if constexpr (!ARM && WPT == 1 && SHARE == 2) {
             const int n_act = (T + 1) >> 1, n_help = 32 - n_act, k = (n_act + n_help - 1) / n_help, lseg = split / k;
             const int tail_end = n_obs - ((n_obs - split) & 3);

@@ -357,10 +357,12 @@ __device__ __forceinline__ void log_switch(const DevParams &p, const int lane, c
 // LIVE: live obstacle updates (fgd_optimize_live): a private obstacle set per team, polled and refreshed in the kernel.
 // HELP: the obstacle loop of a many-obstacle scene is shared with the warp's sample-less lanes (fgd_device.cuh, share_split);
 // the host launches this instance when the split is active, the LIVE instances always carry it.
-template <int WPT, bool STRICT, int KS, int NW, int MINB, bool ARM, int TC, int MODE, int SPEC = 0, bool LIVE = false, bool HELP = LIVE>
+// OC > 0: instance for exactly OC obstacles (the default scene's 11, next to TC = 50): unrolled obstacle loop.
+template <int WPT, bool STRICT, int KS, int NW, int MINB, bool ARM, int TC, int MODE, int SPEC = 0, bool LIVE = false, bool HELP = LIVE, int OC = 0>
 __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __grid_constant__ DevParams p)
 {
     constexpr bool SP = SPEC > 0;
+    static_assert(OC == 0 || (TC > 0 && !LIVE && !HELP && !ARM && WPT == 1 && OC < FGD_SHARE_MIN_OBS), "compile-time obstacle count: the T = TC default instance");
     static_assert(!HELP || (WPT == 1 && !ARM), "helper lanes: single-warp teams, end-effector cost");
     static_assert(!LIVE || (WPT == 1 && !SP), "live obstacle updates: single-warp teams");
     static_assert(!SP || (WPT == 1 && MODE == 0 && NW == SPEC && SPEC <= 8), "speculative line search: BLS, single-warp replicas, one trajectory per CTA");
@@ -400,6 +402,9 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
     int split = (LIVE || SHARE == 0) ? 0 : share_split(T, p.n_obs, ARM);  // LIVE: follows the adopted obstacle set
     if constexpr (SHARE == 0) {
         if (share_split(T, p.n_obs, ARM) > 0) __trap();                    // launched for a scene that needs the HELP twin: a host-side dispatch bug
+    }
+    if constexpr (OC > 0) {
+        if (p.n_obs != OC) __trap();                                       // the OC instance is only valid for exactly OC obstacles
     }
     __shared__ SpecScratch sp_mem;                                          // SPEC only (a few words)
     SpecScratch *sp = &sp_mem;
@@ -494,7 +499,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) fgd_optimize_kernel(const __gri
             Rows<ARM> Rw;
             float loss_c, toc_c;
             int ful_c;
-            cost_phase<WPT, STRICT, ARM, (WPT > 1), LIVE, SHARE>(p, T, sObs, LIVE ? n_obs_live : p.n_obs, G, y1, y2, st.start, st.goal, st.lam_sg, st.lam_jl, Rw, loss_c, toc_c, ful_c,
+            cost_phase<WPT, STRICT, ARM, (WPT > 1), LIVE, SHARE, OC>(p, T, sObs, LIVE ? n_obs_live : p.n_obs, G, y1, y2, st.start, st.goal, st.lam_sg, st.lam_jl, Rw, loss_c, toc_c, ful_c,
                                                                 split, XA, XB);
             PCLK(1);
             bool accept = false;

@@ -785,6 +785,13 @@ __device__ __forceinline__ void obstacle_block(const float2 *__restrict__ obs, c
 #ifndef FGD_OBS_PIPE
 #define FGD_OBS_PIPE 1
 #endif
+#ifndef FGD_UNROLL_PIPE
+#define FGD_UNROLL_PIPE 2        // trips of the pipelined loop per loop iteration (multi-warp teams): 2 measured -3.6 % on config 3, 4 only -2.4 % (profiles/r02zm_unroll.txt)
+#endif
+#ifndef FGD_UNROLL_R4
+#define FGD_UNROLL_R4 1          // blocks of four per loop iteration in the shared obstacle loop (single-warp teams, many obstacles)
+#endif
+constexpr int UNROLL_PIPE = FGD_UNROLL_PIPE, UNROLL_R4 = FGD_UNROLL_R4;
 struct ObsPair { f2 dx[2], dy[2], rr[2]; };
 
 template <bool STRICT>
@@ -843,7 +850,7 @@ __host__ __device__ inline int share_split(int T, int n_obs, bool whole_arm)
 template <bool STRICT>
 __device__ __forceinline__ void obstacle_range4(const float2 *__restrict__ sObs, int o0, const int o1, const f2 x, const f2 y, f2 &sr, f2 &sx, f2 &sy)
 {
-#pragma unroll 1
+#pragma unroll UNROLL_R4
     for (; o0 < o1; o0 += 4) obstacle_block<4, STRICT>(sObs + o0, x, y, sr, sx, sy);
 }
 // the last obstacles [o0, n_obs) one at a time (any alignment; at most three)
@@ -981,7 +988,7 @@ __device__ __forceinline__ void cost_phase(const DevParams &p, const int T, cons
             ObsPair A, B;
             obstacle_pair_head<STRICT>(sObs, px[2], py[2], A);
             o = 2;
-#pragma unroll 1
+#pragma unroll UNROLL_PIPE
             for (; o + 4 <= n_obs; o += 4) {              // two pairs per trip so that A / B never have to be copied
                 obstacle_pair_head<STRICT>(sObs + o, px[2], py[2], B);
                 obstacle_pair_tail(A, sr[0], sx[0], sy[0]);

@@ -75,7 +75,7 @@ typedef struct FgdConfig {
     int32_t n_joints;                    /* --n-joints, must be 3    robot.py:18             */
     int32_t obstacle_capacity;           /* max obstacles the device buffer can hold         */
     int32_t strict_math;                 /* 1: IEEE reciprocal, division and square root - every result bit-identical to the CPU oracle
-                                            (1.13-1.42 x the fast-math time); 0: rcp.approx, Markstein division, MUFU.SQRT */
+                                            (1.11-1.42 x the fast-math time); 0: rcp.approx, Markstein division */
     int32_t max_inner_iteration;         /* optimizer_BLS.py:27                              */
     int32_t max_outer_iteration;         /* optimizer_BLS.py:28                              */
     int32_t max_bls_iteration;           /* optimizer_BLS.py:39                              */
@@ -234,6 +234,10 @@ int fgd_measure_fp32_peak(FgdHandle *h, double *tflops_out, void *stream);
  * one reciprocal per (sample, obstacle) pair), nominal 148 SM x 16 / clk x 1.965 GHz = 4.65. */
 int fgd_measure_mufu_peak(FgdHandle *h, double *trcp_out, void *stream);
 int fgd_abi_version(void);
+/* Host helper (no GPU needed): the smallest float t with sqrtf(t) >= eps.  The kernels evaluate the end-point predicates
+ * ||q[0] - start|| < eps_position, ||v[0]|| < eps_velocity, ... (robot.py:90-101) as  squared norm < t : the correctly
+ * rounded square root is monotonic, so the two tests agree for every input.  Exported for the CPU tests. */
+float fgd_sqrt_threshold(float eps);
 
 #ifdef __cplusplus
 }

@@ -52,6 +52,7 @@ EXPORTED_SYMBOLS = (
     "fgd_obstacle_count", "fgd_obstacle_generation", "fgd_optimize_live", "fgd_eval_cost_grad", "fgd_optimize_bls", "fgd_optimize_gd", "fgd_optimize_host",
     "fgd_argmin_per_problem", "fgd_launch_geometry", "fgd_kernel_launches", "fgd_abi_version",
     "fgd_measure_fp32_peak", "fgd_measure_mufu_peak", "fgd_set_init_basis", "fgd_init_trajectory", "fgd_optimize_host_io", "fgd_zero_copy_calls", "fgd_speculative_launches",
+    "fgd_sqrt_threshold",
 )
 
 _lib = None

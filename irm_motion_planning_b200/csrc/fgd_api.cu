@@ -54,6 +54,17 @@ struct Geometry { int grid, block, smem; };
 // warps per trajectory by trajectory length (each thread owns R = 2 adjacent time samples: TP = 64 * WPT >= T)
 inline int warps_per_trajectory(int T) { return T <= 64 ? 1 : (T <= 128 ? 2 : 4); }
 
+// The smallest float t with sqrtf(t) >= eps.  The correctly rounded square root is monotonic, so for every x >= 0 (and
+// NaN)  sqrtf(x) < eps  <=>  x < t : the kernels test the squared norms against t and never take a square root.
+inline float sqrt_threshold(float eps)
+{
+    if (!(eps > 0.0f)) return 0.0f;                         // sqrtf(x) < eps is never true
+    float t = eps * eps;
+    while (std::sqrt(t) < eps) t = std::nextafter(t, INFINITY);
+    while (t > 0.0f && std::sqrt(std::nextafter(t, 0.0f)) >= eps) t = std::nextafter(t, 0.0f);
+    return t;
+}
+
 // (variant, WPT, KSRC, NW, MINB): the instantiated optimiser kernels.  WPT warps per trajectory; KSRC: where the K tables
 // live - tensor memory (K_TMEM), shared memory (K_SMEM, T <= 64) or L2 (K_L2); NW warps per CTA, MINB = min CTAs per SM
 // (register cap).  Variant 0 is the default: ONE 16-warp CTA per SM with the tables in tensor memory - 16 single-warp teams
@@ -414,6 +425,8 @@ extern "C" {
 
 int fgd_abi_version(void) { return FGD_ABI_VERSION; }
 
+float fgd_sqrt_threshold(float eps) { return sqrt_threshold(eps); }
+
 const char *fgd_status_string(int s)
 {
     switch (s) {
@@ -524,6 +537,7 @@ int fgd_create(const FgdConfig *cfg, FgdHandle **out)
     p.lam_sg0 = cfg->lambda_sg_constraint; p.lam_jl0 = cfg->lambda_jl_constraint; p.lam_inc = cfg->lambda_constraint_increase;
     p.lam_max = cfg->lambda_max_cost; p.lam_reg = cfg->lambda_reg; p.eps_loop = cfg->loop_loss_reduction;
     p.eps_pos = cfg->eps_position; p.eps_vel = cfg->eps_velocity;
+    p.thr_pos = sqrt_threshold(p.eps_pos); p.thr_vel = sqrt_threshold(p.eps_vel);
     p.bls_lr0 = cfg->bls_lr_start; p.bls_alpha = cfg->bls_alpha; p.bls_bp = cfg->bls_beta_plus; p.bls_bm = cfg->bls_beta_minus;
     p.qmax = cfg->max_joint_position; p.qmin = cfg->min_joint_position; p.vmax = cfg->max_joint_velocity;
     for (int i = 0; i < 3; ++i) p.link[i] = cfg->link_length[i];

@@ -39,6 +39,7 @@ enum Kind : int { K_IDLE = 0, K_EVAL0 = 1, K_CAND = 2, K_BACK = 3 };
 struct DevParams {
     int T, TP, n_obs, max_inner, max_outer, max_bls, cvdl, mode, budget, B;
     float lam_sg0, lam_jl0, lam_inc, lam_max, lam_reg, eps_loop, eps_pos, eps_vel;
+    float thr_pos, thr_vel;  // smallest floats whose IEEE square root reaches eps_pos / eps_vel:  sqrt(x) < eps  <=>  x < thr  (host, fgd_create)
     float bls_lr0, bls_alpha, bls_bp, bls_bm;
     float qmax, qmin, vmax;
     float link[3];
@@ -260,19 +261,6 @@ __device__ __forceinline__ float div_T(const DevParams &p, float x)
     } else {
         const float q0 = x * p.inv_T;
         return fmaf(fmaf(-q0, p.fT, x), p.inv_T, q0);
-    }
-}
-
-// sqrt for the end-point norm predicates (robot.py:90-101).  Fast: MUFU.SQRT (1 ulp) instead of the IEEE sequence.
-template <bool STRICT>
-__device__ __forceinline__ float sqrt_norm(float x)
-{
-    if constexpr (STRICT) {
-        return sqrtf(x);
-    } else {
-        float r;
-        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-        return r;
     }
 }
 
@@ -1076,8 +1064,10 @@ __device__ __forceinline__ void cost_phase(const DevParams &p, const int T, cons
     const float sg = (0.5f * ssp0 + 0.5f * sspT) + (0.5f * ssv0 + 0.5f * ssvT);
     const float jl = div_T<STRICT>(p, sum_p) + div_T<STRICT>(p, sum_v);
     loss = fmaf(lam_jl, jl, fmaf(lam_sg, sg, toc));
-    const bool ends_ok = (sqrt_norm<STRICT>(ssp0) < p.eps_pos) && (sqrt_norm<STRICT>(sspT) < p.eps_pos) &&
-                         (sqrt_norm<STRICT>(ssv0) < p.eps_vel) && (sqrt_norm<STRICT>(ssvT) < p.eps_vel);
+    // end-point predicates  ||.|| < eps  (robot.py:90-101) without the square roots: the correctly rounded sqrt is monotonic, so
+    // sqrt(x) < eps  <=>  x < thr with thr = the smallest float whose square root reaches eps (computed on the host with the IEEE
+    // sqrt, fgd_api.cu sqrt_threshold) - exact in both math modes (the oracle takes the square roots)
+    const bool ends_ok = (ssp0 < p.thr_pos) && (sspT < p.thr_pos) && (ssv0 < p.thr_vel) && (ssvT < p.thr_vel);
     ful = (ends_ok && all_ok) ? 1 : 0;
 }
 

@@ -136,3 +136,26 @@ def test_shard_range_partitions_exactly():
             assert parts[0][0] == 0 and parts[-1][1] == n
             assert all(parts[i][1] == parts[i + 1][0] for i in range(w - 1))
             assert max(b - a for a, b in parts) - min(b - a for a, b in parts) <= 1
+
+
+def test_sqrt_threshold_is_equivalent_to_the_square_root_test():
+    """The kernels test the end-point predicates ||.|| < eps (robot.py:90-101) as  squared norm < fgd_sqrt_threshold(eps)
+    (no square root on the device; the oracle takes the IEEE square root): equivalent for every float because the
+    correctly rounded sqrt is monotonic - checked on the floats around the threshold and on random values."""
+    from irm_motion_planning_b200 import backend, build
+    build.build()
+    lib = ctypes.CDLL(backend.LIB_PATH)
+    lib.fgd_sqrt_threshold.restype = ctypes.c_float
+    lib.fgd_sqrt_threshold.argtypes = [ctypes.c_float]
+    f = np.float32
+    rng = np.random.default_rng(0)
+    for eps in [0.01, 0.05, 1e-3, 0.1, 1.0, 7.0, 1e-20, 1e15] + list(np.exp(rng.uniform(-20, 5, 100))):
+        e = f(eps)
+        t = f(lib.fgd_sqrt_threshold(e))
+        lo, hi, xs = t, t, [t]
+        for _ in range(200):
+            lo, hi = np.nextafter(lo, f(0)), np.nextafter(hi, f(np.inf))
+            xs += [lo, hi]
+        xs = np.concatenate([np.array(xs, f), (np.abs(rng.standard_normal(5000)) * float(e) ** 2 * 4).astype(f), np.array([0.0, np.inf, np.nan], f)])
+        assert np.array_equal(np.sqrt(xs) < e, xs < t), eps
+    assert lib.fgd_sqrt_threshold(f(0.0)) == 0.0 and lib.fgd_sqrt_threshold(f(-1.0)) == 0.0
